@@ -1,0 +1,100 @@
+/* rnnt_b200 -- C ABI of the B200 (sm_100a) joint-network + transducer-loss hot path.
+ *
+ * Drop-in boundary for the reference's Python-level interface (jakepoz/rnnt has no FFI of its own):
+ *   rnnt/joint.py:25-39   JointNetwork.forward            -> rnnt_b200_joint_loss_fwd/bwd (fused, no logits)
+ *   rnnt/joint.py:44-55   JointNetwork.single_forward     -> rnnt_b200_joint_argmax (decode step)
+ *   rnnt/model.py:35-41   torchaudio.functional.rnnt_loss -> rnnt_b200_joint_loss_fwd/bwd, or
+ *                                                            rnnt_b200_loss_dense_fwd/bwd when logits exist
+ *   rnnt/model.py:66-69, 110-113  joint step + argmax of greedy decode -> rnnt_b200_joint_argmax
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless stated otherwise; the caller owns every buffer, including the
+ *     workspace.  The library allocates nothing persistent and keeps no references after a call returns.
+ *   - Work is enqueued on `stream` (a cudaStream_t); no call synchronises the device.  Re-entrant.
+ *   - Return 0 on success, a negative code for invalid arguments / unsupported shapes (no CPU fallback:
+ *     unsupported means error), a positive cudaError_t value for CUDA failures.
+ *     rnnt_b200_last_error() returns the message for the calling thread.
+ *   - Lattice tensors use the reference layout: (B, T, U1) row-major with U1 = max target length + 1;
+ *     targets are (B, U1-1) int32; lengths are int32; blank < 0 means V + blank (the reference passes -1).
+ */
+#ifndef RNNT_B200_H_
+#define RNNT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNNT_B200_ABI_VERSION 1
+
+int rnnt_b200_abi_version(void);
+const char* rnnt_b200_last_error(void);
+
+/* Upper bound on the number of 16(t) x 8(u) lattice tiles of a (B,T,U1) batch. */
+int64_t rnnt_b200_max_tiles(int B, int T, int U1);
+
+/* Workspace sizes in bytes.  ring_tiles = number of 128-cell tiles the backward's bf16 gradient / activation
+ * rings hold at once (fixed size, independent of B*T*U1); the backward walks the batch in chunks of that size. */
+int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, size_t* fwd_bytes,
+                              size_t* bwd_bytes);
+
+/* Fused joint + loss forward.  Replaces rnnt/joint.py:25-39 followed by rnnt/model.py:35-41 (reduction="none").
+ *   enc  (B,T,H) fp32 with element strides (enc_sb, enc_st, 1)      pred (B,U1,H) fp32 contiguous
+ *   W    (V,H) fp32 (joint_ln.weight)                                bias (V) fp32 (joint_ln.bias)
+ * Outputs (all fully written for valid cells): costs (B), lp (B,T,U1,2) = log p(blank), log p(label),
+ * lse (B,T,U1), alpha (B,T,U1), beta (B,T,U1).  These five are the residuals the backward consumes.
+ * status (optional, may be NULL): device int set to 1 if any length is out of range. */
+int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
+                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int H, int V, int blank, float* costs, float* lp, float* lse,
+                             float* alpha, float* beta, int32_t* status, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/* Fused backward.  Replaces RnntLoss.backward + autograd through rnnt/joint.py:32-39.
+ * dcost (B) = d loss / d cost_b (1/B for reduction="mean"); clamp <= 0 disables gradient clamping.
+ * Outputs are overwritten: d_enc (B,T,H) contiguous, d_pred (B,U1,H), dW (V,H), dbias (V), all fp32. */
+int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
+                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
+                             const float* alpha, const float* beta, const float* dcost, float clamp, float* d_enc,
+                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Loss on already materialised logits (B,T,U1,V) fp32 contiguous -- the literal torchaudio.functional.rnnt_loss
+ * call of rnnt/model.py:35-41 for callers that hold logits (e.g. eval.py:76 style uses).  fwd writes costs and the
+ * residuals; bwd writes grads (B,T,U1,V) = d loss / d logits (zeros on padding).  scratch_coef: (B,T,U1,4) fp32. */
+int rnnt_b200_loss_dense_fwd(const float* logits, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int V, int blank, float* costs, float* lp, float* lse,
+                             float* alpha, float* beta, void* stream);
+int rnnt_b200_loss_dense_bwd(const float* logits, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int V, int blank, const float* lp, const float* lse,
+                             const float* alpha, const float* beta, const float* dcost, float clamp,
+                             float* scratch_coef, float* grads, void* stream);
+
+/* Lattice only: alpha/beta/costs from log-probs (B,T,U1,2). */
+int rnnt_b200_lattice(const float* lp, const int32_t* T_len, const int32_t* U_len, int B, int T, int U1, float* alpha,
+                      float* beta, float* costs, void* stream);
+
+/* Greedy-decode joint step (fp32): tokens[n] = argmax_v(W . tanh(enc_rows[n] + pred_rows[n]) + bias), lowest index
+ * on ties; margin[n] (optional) = top1 - top2 logit.  Row n of enc_rows / pred_rows starts at n * stride floats.
+ * scratch: rnnt_b200_joint_argmax_scratch_bytes(N, V) bytes. */
+size_t rnnt_b200_joint_argmax_scratch_bytes(int N, int V);
+int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const float* pred_rows, int64_t pred_stride,
+                           const float* W, const float* bias, int N, int H, int V, int32_t* tokens, float* margin,
+                           void* scratch, void* stream);
+
+/* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
+ *   offsets[0] tile table (B+1 int32 prefix sums of tiles per utterance, then one status int)
+ *   offsets[1] W as bf16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
+ *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] bf16
+ *   offsets[5] activation ring h [ring_tiles*128, Hp] bf16     offsets[6] total bytes.
+ * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
+int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int64_t* offsets /*[8]*/,
+                              int* Hp, int* Vp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNNT_B200_H_ */

@@ -1,0 +1,264 @@
+// C-ABI entry points (see include/rnnt_b200.h).  Plain pointers and sizes only; every buffer is caller-owned.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "../../include/rnnt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+using rb::kTileM;
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t tile_off, wb, bias2, coef, g_ring, h_ring, total_fwd, total_bwd;
+  int Hp, Vp;
+};
+
+WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles) {
+  WsLayout w;
+  w.Hp = round_up(H, 64);
+  w.Vp = round_up(V, 256);
+  size_t off = 0;
+  w.tile_off = off; off = align_up(off + (static_cast<size_t>(B) + 2) * sizeof(int), 1024);
+  w.wb = off;       off = align_up(off + static_cast<size_t>(w.Vp) * w.Hp * 2, 1024);
+  w.bias2 = off;    off = align_up(off + static_cast<size_t>(w.Vp) * 4, 1024);
+  w.total_fwd = off;
+  w.coef = off;     off = align_up(off + static_cast<size_t>(B) * T * U1 * 16, 1024);
+  const size_t ring_rows = static_cast<size_t>(ring_tiles) * kTileM;
+  w.g_ring = off;   off = align_up(off + ring_rows * w.Vp * 2, 1024);
+  w.h_ring = off;   off = align_up(off + ring_rows * w.Hp * 2, 1024);
+  w.total_bwd = off;
+  return w;
+}
+
+int check_common(const void* enc, int64_t enc_sb, int64_t enc_st, const void* pred, int B, int T, int U1, int H,
+                 int V, int* blank) {
+  RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && H > 0 && V > 1, -1, "invalid shape B=%d T=%d U1=%d H=%d V=%d", B, T, U1, H, V);
+  RB_REQUIRE(H % 8 == 0, -2, "hidden_features must be a multiple of 8 (got %d)", H);
+  RB_REQUIRE(U1 <= 1024, -5, "U+1 must be <= 1024 (got %d)", U1);
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(enc) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred) & 15) == 0, -3,
+             "enc/pred must be 16-byte aligned");
+  RB_REQUIRE(enc_st % 2 == 0 && enc_sb % 2 == 0 && enc_st >= H, -3,
+             "audio features must be contiguous in the feature dimension with even strides");
+  if (*blank < 0) *blank += V;
+  RB_REQUIRE(*blank >= 0 && *blank < V, -4, "blank index out of range");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rnnt_b200_abi_version(void) { return RNNT_B200_ABI_VERSION; }
+const char* rnnt_b200_last_error(void) { return rb::get_error(); }
+
+int64_t rnnt_b200_max_tiles(int B, int T, int U1) {
+  return static_cast<int64_t>(B) * ((T + rb::kTileT - 1) / rb::kTileT) * ((U1 + rb::kTileU - 1) / rb::kTileU);
+}
+
+int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, size_t* fwd_bytes,
+                              size_t* bwd_bytes) {
+  RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && H > 0 && V > 1 && ring_tiles >= 0, -1, "invalid shape");
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
+  if (fwd_bytes) *fwd_bytes = w.total_fwd;
+  if (bwd_bytes) *bwd_bytes = w.total_bwd;
+  return 0;
+}
+
+int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int64_t* offsets, int* Hp,
+                              int* Vp) {
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
+  offsets[0] = w.tile_off; offsets[1] = w.wb; offsets[2] = w.bias2; offsets[3] = w.coef;
+  offsets[4] = w.g_ring; offsets[5] = w.h_ring; offsets[6] = w.total_bwd; offsets[7] = w.total_fwd;
+  if (Hp) *Hp = w.Hp;
+  if (Vp) *Vp = w.Vp;
+  return 0;
+}
+
+int rnnt_b200_lattice(const float* lp, const int32_t* T_len, const int32_t* U_len, int B, int T, int U1, float* alpha,
+                      float* beta, float* costs, void* stream) {
+  RB_REQUIRE(B > 0 && T > 0 && U1 > 0, -1, "invalid shape");
+  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, static_cast<cudaStream_t>(stream));
+}
+
+int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
+                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int H, int V, int blank, float* costs, float* lp, float* lse,
+                             float* alpha, float* beta, int32_t* status, void* workspace, size_t workspace_bytes,
+                             void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
+  if (rc) return rc;
+  const WsLayout w = ws_layout(B, T, U1, H, V, 0);
+  RB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total_fwd, -7, "workspace too small: need %zu bytes",
+             w.total_fwd);
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7, "workspace must be 256-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* tile_off = reinterpret_cast<int*>(ws + w.tile_off);
+  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(ws + w.wb);
+  float* bias2 = reinterpret_cast<float*>(ws + w.bias2);
+
+  rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, status, stream);
+  if (rc) return rc;
+  rc = rb::launch_convert_weights(W, bias, V, H, w.Vp, w.Hp, Wb, bias2, stream);
+  if (rc) return rc;
+
+  CUtensorMap tmW;
+  rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
+  if (rc) return rc;
+
+  rb::JointArgs a{};
+  a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st;
+  a.pred = pred; a.pred_sb = static_cast<long long>(U1) * H; a.pred_su = H;
+  a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
+  a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
+  a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
+  a.tile_begin = 0; a.tile_cap = 0x3fffffff;
+  a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.clamp = 0.f;
+  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
+  const int grid = static_cast<int>(std::min<int64_t>(rb::device_sm_count(), max_tiles));
+  rc = rb::launch_joint_gemm(0, tmW, tmW, tmW, a, grid, stream);
+  if (rc) return rc;
+  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
+}
+
+int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
+                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
+                             const float* alpha, const float* beta, const float* dcost, float clamp, float* d_enc,
+                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, void* workspace,
+                             size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
+  if (rc) return rc;
+  RB_REQUIRE(ring_tiles >= 1 && ring_tiles * kTileM < (1ll << 30), -8, "ring_tiles out of range");
+  RB_REQUIRE(H % 4 == 0, -2, "hidden_features must be a multiple of 4");
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
+  RB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total_bwd, -7, "workspace too small: need %zu bytes",
+             w.total_bwd);
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7, "workspace must be 256-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int* tile_off = reinterpret_cast<int*>(ws + w.tile_off);
+  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(ws + w.wb);
+  float* bias2 = reinterpret_cast<float*>(ws + w.bias2);
+  float4* coef = reinterpret_cast<float4*>(ws + w.coef);
+  __nv_bfloat16* g_ring = reinterpret_cast<__nv_bfloat16*>(ws + w.g_ring);
+  __nv_bfloat16* h_ring = reinterpret_cast<__nv_bfloat16*>(ws + w.h_ring);
+  const uint64_t ring_rows = static_cast<uint64_t>(ring_tiles) * kTileM;
+
+  RB_CUDA_CHECK(cudaMemsetAsync(d_enc, 0, static_cast<size_t>(B) * T * H * 4, stream));
+  RB_CUDA_CHECK(cudaMemsetAsync(d_pred, 0, static_cast<size_t>(B) * U1 * H * 4, stream));
+  RB_CUDA_CHECK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * 4, stream));
+  RB_CUDA_CHECK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream));
+
+  rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, nullptr, stream);
+  if (rc) return rc;
+  rc = rb::launch_convert_weights(W, bias, V, H, w.Vp, w.Hp, Wb, bias2, stream);
+  if (rc) return rc;
+  rc = rb::launch_coef(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef, stream);
+  if (rc) return rc;
+
+  CUtensorMap tmW, tmWmn, tmGst, tmHst, tmGmn, tmHmn;
+  // W [Vp, Hp]: K-major boxes (64 k x 256 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
+  rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmWmn, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
+  if (rc) return rc;
+  // rings: 64 x 128 boxes for the tile stores and the K-major dh operand, 64 x 64 boxes for the MN-major dW operands
+  rc = rb::make_tmap_2d(&tmGst, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 128);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmHst, h_ring, 2, w.Hp, ring_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmGmn, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 64);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmHmn, h_ring, 2, w.Hp, ring_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
+  if (rc) return rc;
+
+  const int sms = rb::device_sm_count();
+  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
+  const int64_t nchunks = (max_tiles + ring_tiles - 1) / ring_tiles;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int tile_begin = static_cast<int>(c * ring_tiles);
+    const int64_t chunk_tiles = std::min<int64_t>(ring_tiles, max_tiles - c * ring_tiles);
+    const int grid = static_cast<int>(std::min<int64_t>(sms, chunk_tiles));
+
+    rb::JointArgs a{};
+    a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st;
+    a.pred = pred; a.pred_sb = static_cast<long long>(U1) * H; a.pred_su = H;
+    a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
+    a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
+    a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
+    a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles);
+    a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.clamp = clamp;
+    rc = rb::launch_joint_gemm(1, tmW, tmGst, tmHst, a, grid, stream);
+    if (rc) return rc;
+
+    rb::DhArgs d{};
+    d.h_ring = h_ring; d.T_len = T_len; d.U_len = U_len; d.tile_off = tile_off;
+    d.B = B; d.T = T; d.U1 = U1; d.H = H; d.Hp = w.Hp; d.Vp = w.Vp;
+    d.tile_begin = tile_begin; d.tile_cap = static_cast<int>(ring_tiles);
+    d.d_enc = d_enc; d.d_pred = d_pred; d.dbg_dh = nullptr;
+    rc = rb::launch_dh_gemm(tmGst, tmWmn, d, grid, stream);
+    if (rc) return rc;
+
+    rb::DwArgs g{};
+    g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
+    g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW;
+    const int out_tiles = (w.Vp / kTileM) * ((((w.Hp + 255) / 256) + 1) / 2);
+    const int64_t kchunks = chunk_tiles * 2;
+    g.ksplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms / std::max(1, out_tiles), kchunks)));
+    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, stream);
+    if (rc) return rc;
+    rc = rb::launch_db(g_ring, tile_off, B, tile_begin, static_cast<int>(ring_tiles), V, w.Vp, dbias, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int rnnt_b200_loss_dense_fwd(const float* logits, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int V, int blank, float* costs, float* lp, float* lse,
+                             float* alpha, float* beta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && V > 1, -1, "invalid shape");
+  RB_REQUIRE(U1 <= 1024, -5, "U+1 must be <= 1024 (got %d)", U1);
+  if (blank < 0) blank += V;
+  RB_REQUIRE(blank >= 0 && blank < V, -4, "blank index out of range");
+  int rc = rb::launch_dense_logprobs(logits, targets, U1 - 1, T_len, U_len, B, T, U1, V, blank, lp, lse, stream);
+  if (rc) return rc;
+  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
+}
+
+int rnnt_b200_loss_dense_bwd(const float* logits, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
+                             int B, int T, int U1, int V, int blank, const float* lp, const float* lse,
+                             const float* alpha, const float* beta, const float* dcost, float clamp,
+                             float* scratch_coef, float* grads, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && V > 1, -1, "invalid shape");
+  if (blank < 0) blank += V;
+  RB_REQUIRE(blank >= 0 && blank < V, -4, "blank index out of range");
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(scratch_coef) & 15) == 0, -3, "scratch_coef must be 16-byte aligned");
+  // clamp acts on d cost / d logits before the dcost scaling (torchaudio ComputeGradients).
+  RB_REQUIRE(!(clamp > 0.f && dcost != nullptr), -9,
+             "dense backward: clamp > 0 requires dcost == NULL (scale the returned gradients by dcost instead)");
+  float4* coef = reinterpret_cast<float4*>(scratch_coef);
+  int rc = rb::launch_coef(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef, stream);
+  if (rc) return rc;
+  return rb::launch_dense_grads(logits, targets, U1 - 1, T_len, U_len, coef, B, T, U1, V, blank, clamp, grads, stream);
+}
+
+size_t rnnt_b200_joint_argmax_scratch_bytes(int N, int V) { return rb::joint_argmax_scratch_bytes(N, V); }
+
+int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const float* pred_rows, int64_t pred_stride,
+                           const float* W, const float* bias, int N, int H, int V, int32_t* tokens, float* margin,
+                           void* scratch, void* stream) {
+  RB_REQUIRE(N >= 0 && H > 0 && V > 0, -1, "invalid shape");
+  return rb::launch_joint_argmax(enc_rows, enc_stride, pred_rows, pred_stride, W, bias, N, H, V, tokens, margin,
+                                 static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// Backward contraction #3:  dW = g^T . h  (K = lattice cells of the current ring chunk).
+//
+// Replaces the weight-gradient GEMM of joint_ln's autograd backward (rnnt/joint.py:39).
+// Both operands are read as MN-major views of the row-major rings written by the G-mode joint kernel:
+//   A[m=v][k=c] = g_ring[c][v]      B[n=kh][k=c] = h_ring[c][kh]
+// One CTA owns a 128(v) x 512(k_h) block of dW (two TMEM accumulators = all 512 columns) for one K split and
+// adds it into the fp32 dW with vector reductions (red.global.add.v4.f32).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rb {
+namespace {
+
+constexpr int kStagesA = 4;
+constexpr int kStagesB = 4;
+constexpr int kBytesA = kBK * kTileM * 2;   // 16 KB: 64 cells x 128 v  (two 64x64 boxes)
+constexpr int kBytesB = kBK * kBN * 2;      // 32 KB: 64 cells x 256 kh (four 64x64 boxes)
+constexpr int kNumThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct SmemLayout {
+  static constexpr int b_ring = 0;
+  static constexpr int a_ring = b_ring + kStagesB * kBytesB;
+  static constexpr int bars = a_ring + kStagesA * kBytesA;
+  static constexpr int total = bars + 256;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant__ CUtensorMap tmHmn, DwArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t b_ring = smem_base + SmemLayout::b_ring;
+  const uint32_t a_ring = smem_base + SmemLayout::a_ring;
+  const uint32_t bars = smem_base + SmemLayout::bars;
+  const uint32_t b_full = bars, b_empty = bars + 8 * kStagesB;
+  const uint32_t a_full = bars + 16 * kStagesB, a_empty = a_full + 8 * kStagesA;
+  const uint32_t tmem_full = a_empty + 8 * kStagesA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = __ldg(p.tile_off + p.B);
+  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
+  const int nkc = max(0, tile_end - p.tile_begin) * (kTileM / kBK);   // 64-row K chunks in this ring chunk
+
+  const int nblk_total = (p.Hp + kBN - 1) / kBN;
+  const int nht = (nblk_total + 1) / 2;
+  const int nvt = p.Vp / kTileM;
+  int bid = blockIdx.x;
+  const int vt = bid % nvt; bid /= nvt;
+  const int ht = bid % nht; bid /= nht;
+  const int ks = bid;
+  const int nblk = min(2, nblk_total - ht * 2);
+  const int k_begin = static_cast<int>(static_cast<long long>(nkc) * ks / p.ksplit);
+  const int k_end = static_cast<int>(static_cast<long long>(nkc) * (ks + 1) / p.ksplit);
+  if (k_begin >= k_end) return;   // uniform over the CTA
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmGmn);
+    tma_prefetch_desc(&tmHmn);
+    for (int s = 0; s < kStagesB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < kStagesA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t ita = 0, itb = 0;
+      for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
+        const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
+        mbar_wait(a_empty + 8 * sa, pha ^ 1);
+        mbar_expect_tx(a_full + 8 * sa, kBytesA);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d(a_ring + sa * kBytesA + j * 8192, &tmGmn, a_full + 8 * sa, vt * kTileM + j * 64, kc * kBK);
+        for (int blk = 0; blk < nblk; ++blk, ++itb) {
+          const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
+          mbar_wait(b_empty + 8 * sb, phb ^ 1);
+          mbar_expect_tx(b_full + 8 * sb, kBytesB);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tma_load_2d(b_ring + sb * kBytesB + j * 8192, &tmHmn, b_full + 8 * sb,
+                        (ht * 2 + blk) * kBN + j * 64, kc * kBK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM, kBN, 1, 1);
+    uint32_t ita = 0, itb = 0;
+    for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
+      const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
+      mbar_wait(a_full + 8 * sa, pha);
+      for (int blk = 0; blk < nblk; ++blk, ++itb) {
+        const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
+        mbar_wait(b_full + 8 * sb, phb);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = a_ring + sa * kBytesA, b_addr = b_ring + sb * kBytesB;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);   // MN-major
+            const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);   // MN-major
+            umma_f16(tmem_base + blk * kBN, ad, bd, idesc, (kc > k_begin) || (k != 0));
+          }
+          umma_commit(b_empty + 8 * sb);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(a_empty + 8 * sa);
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(tmem_full);
+    __syncwarp();
+  } else {
+    const int lane_grp = warp & 3;
+    const int row = lane_grp * 32 + lane;
+    const int v = vt * kTileM + row;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int c32 = 0; c32 < nblk * (kBN / 32); ++c32) {
+      const int col0 = ht * 2 * kBN + c32 * 32;
+      if (col0 >= p.H) break;
+      float acc[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + c32 * 32, acc);
+      tmem_ld_wait();
+      if (v < p.V) {
+        float* dst = p.dW + static_cast<long long>(v) * p.H + col0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (col0 + 4 * q + 3 < p.H) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(acc[4 * q]),
+                         "f"(acc[4 * q + 1]), "f"(acc[4 * q + 2]), "f"(acc[4 * q + 3])
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col0 + 4 * q + e < p.H) atomicAdd(dst + 4 * q + e, acc[4 * q + e]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// db[v] = sum over ring rows of g[row, v]
+__global__ void db_kernel(const __nv_bfloat16* __restrict__ g_ring, const int* __restrict__ tile_off, int B,
+                          int tile_begin, int tile_cap, int V, int Vp, float* __restrict__ db) {
+  const int total_tiles = __ldg(tile_off + B);
+  const int tile_end = min(total_tiles, tile_begin + tile_cap);
+  const int nrows = max(0, tile_end - tile_begin) * kTileM;
+  const int col = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (col >= Vp) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = blockIdx.y * nw + wid; r < nrows; r += gridDim.y * nw) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(g_ring + static_cast<long long>(r) * Vp + col));
+    s0 += bf16lo_to_f32(w);
+    s1 += bf16hi_to_f32(w);
+  }
+  if (col < V) atomicAdd(db + col, s0);
+  if (col + 1 < V) atomicAdd(db + col + 1, s1);
+}
+
+}  // namespace
+
+int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream) {
+  const size_t smem = SmemLayout::total + 1024;
+  RB_CUDA_CHECK(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblk_total = (args.Hp + kBN - 1) / kBN;
+  const int grid = (args.Vp / kTileM) * ((nblk_total + 1) / 2) * args.ksplit;
+  dw_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmGmn, tmHmn, args);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_db(const __nv_bfloat16* g_ring, const int* tile_off, int B, int tile_begin, int tile_cap, int V, int Vp,
+              float* db, cudaStream_t stream) {
+  dim3 grid((Vp / 2 + 31) / 32, 64);
+  db_kernel<<<grid, 256, 0, stream>>>(g_ring, tile_off, B, tile_begin, tile_cap, V, Vp, db);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rb

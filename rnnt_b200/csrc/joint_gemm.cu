@@ -1,0 +1,384 @@
+// Fused joint GEMM kernel (forward "F" and backward-recompute "G" modes).
+//
+// Replaces rnnt/joint.py:32-39 (broadcast add + tanh + joint_ln) fused with the first half of
+// torchaudio's rnnt_loss (ReduceMax2D / ReduceLogSumExpGivenMax2D / ComputeLogProbs, reference call
+// site rnnt/model.py:35-41) in F mode, and with ComputeGradients in G mode.  The (B,T,U1,V) logit
+// tensor only ever exists as fp32 accumulators in TMEM.
+//
+//   logits[c, v] = sum_k bf16(tanh(enc[b,t,k] + pred[b,u,k])) * bf16(W[v,k])  (+ bias[v] in the epilogue)
+//
+// Warp roles (480 threads, 1 CTA / SM, persistent over 16(t)x8(u) lattice tiles):
+//   warp 0      TMA producer: W tiles (256 rows x 64 k, 128B-swizzled) into a 4-stage ring
+//   warp 1      tcgen05.mma issuer (M=128, N=256, K=16; two 256-column accumulators per N pass)
+//   warps 2-5   epilogue: tcgen05.ld -> online log-sum-exp + blank/label gather (F) or
+//               softmax*gamma - one-hots -> bf16 -> smem -> TMA store into the gradient ring (G)
+//   warps 6-13  A-operand producers: tanh(enc+pred) -> bf16 -> swizzled smem (4-stage ring)
+//   warp 14     (G mode) TMA-stores each finished A stage into the hidden-activation ring
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rb {
+
+namespace {
+
+constexpr int kStagesA = 4;
+constexpr int kStagesB = 4;
+constexpr int kBytesA = kTileM * kBK * 2;  // 16 KB
+constexpr int kBytesB = kBN * kBK * 2;     // 32 KB
+constexpr int kBytesG = kTileM * 64 * 2;   // 16 KB staging box for the gradient ring store
+constexpr int kNumThreads = 480;
+constexpr int kFirstEpiWarp = 2;
+constexpr int kFirstProdWarp = 6;
+constexpr int kNumProdWarps = 8;
+constexpr int kStoreWarp = 14;
+constexpr int kTmemCols = 512;
+
+struct SmemLayout {
+  // offsets from the 1024-aligned base
+  static constexpr int b_ring = 0;
+  static constexpr int a_ring = b_ring + kStagesB * kBytesB;
+  static constexpr int g_stage = a_ring + kStagesA * kBytesA;
+  static constexpr int bars = g_stage + 2 * kBytesG;
+  static constexpr int total = bars + 256;
+};
+
+}  // namespace
+
+size_t joint_gemm_smem_bytes() { return SmemLayout::total + 1024; }
+
+template <int MODE>  // 0 = forward (lse + gather), 1 = backward recompute (gradient ring)
+__global__ void __launch_bounds__(kNumThreads, 1)
+joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG,
+                  const __grid_constant__ CUtensorMap tmHr, JointArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t b_ring = smem_base + SmemLayout::b_ring;
+  const uint32_t a_ring = smem_base + SmemLayout::a_ring;
+  const uint32_t g_stage = smem_base + SmemLayout::g_stage;
+  const uint32_t bars = smem_base + SmemLayout::bars;
+  // barrier map (8 bytes each)
+  const uint32_t b_full = bars, b_empty = bars + 8 * kStagesB;
+  const uint32_t a_full = bars + 16 * kStagesB, a_empty = a_full + 8 * kStagesA;
+  const uint32_t tmem_full = a_empty + 8 * kStagesA, tmem_empty = tmem_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int total_tiles = __ldg(p.tile_off + p.B);
+  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
+  const int nk = p.Hp / kBK;
+  const int nblk_total = p.Vp / kBN;
+  const int npass = (nblk_total + 1) / 2;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW);
+    if (MODE == 1) {
+      tma_prefetch_desc(&tmG);
+      tma_prefetch_desc(&tmHr);
+    }
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < kStagesA; ++s) {
+      mbar_init(a_full + 8 * s, kNumProdWarps);
+      mbar_init(a_empty + 8 * s, MODE == 1 ? 2 : 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (W tiles)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        for (int pass = 0; pass < npass; ++pass) {
+          const int nblk = min(2, nblk_total - pass * 2);
+          for (int kc = 0; kc < nk; ++kc) {
+            for (int blk = 0; blk < nblk; ++blk, ++it) {
+              const uint32_t s = it % kStagesB, ph = (it / kStagesB) & 1;
+              mbar_wait(b_empty + 8 * s, ph ^ 1);
+              mbar_expect_tx(b_full + 8 * s, kBytesB);
+              tma_load_2d(b_ring + s * kBytesB, &tmW, b_full + 8 * s, kc * kBK, (pass * 2 + blk) * kBN);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kTileM, kBN, 0, 0);
+    uint32_t ita = 0, itb = 0, pc = 0;
+    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int pass = 0; pass < npass; ++pass, ++pc) {
+        const int nblk = min(2, nblk_total - pass * 2);
+        mbar_wait(tmem_empty, (pc & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < nk; ++kc, ++ita) {
+          const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
+          mbar_wait(a_full + 8 * sa, pha);
+          for (int blk = 0; blk < nblk; ++blk, ++itb) {
+            const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
+            mbar_wait(b_full + 8 * sb, phb);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = a_ring + sa * kBytesA, b_addr = b_ring + sb * kBytesB;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+                const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+                umma_f16(tmem_base + blk * kBN, ad, bd, idesc, (kc | k) != 0);
+              }
+              umma_commit(b_empty + 8 * sb);
+            }
+            __syncwarp();
+          }
+          if (lane == 0) umma_commit(a_empty + 8 * sa);
+          __syncwarp();
+        }
+        if (lane == 0) umma_commit(tmem_full);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kFirstEpiWarp && warp < kFirstProdWarp) {
+    // ===================================================================== epilogue
+    const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = lane_grp * 32 + lane;
+    const int ti = row >> 3, ui = row & 7;
+    const int epi_tid = (warp - kFirstEpiWarp) * 32 + lane;
+    uint32_t pc = 0;
+    uint32_t box_count = 0;
+    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
+      const int t = tc.t0 + ti, u = tc.u0 + ui;
+      const bool valid = (t < tc.Tb) && (u <= tc.Ub);
+      const long long cell = (static_cast<long long>(tc.b) * p.T + min(t, p.T - 1)) * p.U1 + min(u, p.U1 - 1);
+      int tgt = -1;
+      if (valid && u < tc.Ub) tgt = __ldg(p.targets + static_cast<long long>(tc.b) * p.tgt_ld + u);
+      // F state (log2 units)
+      float m = -INFINITY, ssum = 0.f, x_tgt = 0.f, x_blank = 0.f;
+      // G state
+      float gam = 0.f, eB = 0.f, eE = 0.f, lse2 = 1e30f, cbound = 0.f;
+      if (MODE == 1 && valid) {
+        const float4 c4 = __ldg(p.coef + cell);
+        gam = c4.x; eB = c4.y; eE = c4.z; lse2 = c4.w * kLog2e;
+        if (p.clamp > 0.f) cbound = p.clamp * fabsf(p.dcost ? __ldg(p.dcost + tc.b) : 1.f);
+      }
+      const int ring_row0 = (tile - p.tile_begin) * kTileM;
+
+      for (int pass = 0; pass < npass; ++pass, ++pc) {
+        const int nblk = min(2, nblk_total - pass * 2);
+        mbar_wait(tmem_full, pc & 1);
+        tc_fence_after();
+        for (int c32 = 0; c32 < nblk * (kBN / 32); ++c32) {
+          const int col0 = pass * 2 * kBN + c32 * 32;  // global column of v[0]
+          float v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + c32 * 32, v);
+          tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + col0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = __ldg(b4 + q);
+            v[4 * q + 0] = fmaf(v[4 * q + 0], kLog2e, bb.x);
+            v[4 * q + 1] = fmaf(v[4 * q + 1], kLog2e, bb.y);
+            v[4 * q + 2] = fmaf(v[4 * q + 2], kLog2e, bb.z);
+            v[4 * q + 3] = fmaf(v[4 * q + 3], kLog2e, bb.w);
+          }
+          if (MODE == 0) {
+            float cmax = v[0];
+#pragma unroll
+            for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+            const float m_new = fmaxf(m, cmax);
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              acc += ex2_approx(v[j] - m_new);
+              if (col0 + j == tgt) x_tgt = v[j];
+            }
+            ssum = ssum * ex2_approx(m - m_new) + acc;
+            m = m_new;
+            if (p.blank >= col0 && p.blank < col0 + 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == p.blank) x_blank = v[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float g = ex2_approx(v[j] - lse2) * gam;
+              if (col0 + j == tgt) g -= eE;
+              v[j] = g;
+            }
+            if (p.blank >= col0 && p.blank < col0 + 32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j == p.blank) v[j] -= eB;
+            }
+            if (p.clamp > 0.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -cbound), cbound);
+            }
+            // stage bf16 into the 128 x 64 swizzled box (two 32-column halves per box)
+            const uint32_t buf = g_stage + (box_count & 1) * kBytesG;
+            if ((c32 & 1) == 0) {
+              // the TMA store that last used this buffer (two boxes ago) must have finished reading it
+              if (epi_tid == 0) tma_store_wait_read<1>();
+              named_bar_sync(1, 128);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t w0 = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+              const uint32_t w1 = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+              const uint32_t w2 = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+              const uint32_t w3 = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              const uint32_t chunk = (c32 & 1) * 4 + q;
+              const uint32_t addr = buf + row * 128 + ((chunk ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2),
+                           "r"(w3)
+                           : "memory");
+            }
+            if ((c32 & 1) == 1) {
+              fence_proxy_async();
+              named_bar_sync(1, 128);
+              if (epi_tid == 0) {
+                tma_store_2d(&tmG, buf, pass * 2 * kBN + (c32 >> 1) * 64, ring_row0);
+                tma_store_commit();
+              }
+              ++box_count;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+      }
+      if (MODE == 0 && valid) {
+        const float l2 = m + lg2_approx(ssum);
+        p.lse[cell] = l2 * kLn2;
+        float2 o;
+        o.x = (x_blank - l2) * kLn2;
+        o.y = (tgt >= 0) ? (x_tgt - l2) * kLn2 : 0.f;
+        reinterpret_cast<float2*>(p.lp)[cell] = o;
+      }
+    }
+    if (MODE == 1 && epi_tid == 0) tma_store_wait_all<0>();
+  } else if (warp >= kFirstProdWarp && warp < kFirstProdWarp + kNumProdWarps) {
+    // ===================================================================== A producers
+    const int rg = warp - kFirstProdWarp;  // rows rg*16 .. rg*16+15  <->  t-rows 2rg, 2rg+1, all 8 u
+    const int kp = lane;                   // column pair within the 64-wide K chunk
+    uint32_t it = 0;
+    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
+      const float* e_ptr[2];
+      const float* p_ptr[8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + 2 * rg + i, p.T - 1)) * p.enc_st;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        p_ptr[j] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + j, p.U1 - 1)) * p.pred_su;
+
+      float2 e_cur[2], p_cur[8];
+      auto load_chunk = [&](int kc, float2 (&e)[2], float2 (&q)[8]) {
+        const int col = kc * kBK + 2 * kp;
+        if (col < p.H) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) e[i] = __ldg(reinterpret_cast<const float2*>(e_ptr[i] + col));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) q[j] = __ldg(reinterpret_cast<const float2*>(p_ptr[j] + col));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) e[i] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) q[j] = make_float2(0.f, 0.f);
+        }
+      };
+      load_chunk(0, e_cur, p_cur);
+      for (int pass = 0; pass < npass; ++pass) {
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          float2 e_nxt[2], p_nxt[8];
+          const int kn = (kc + 1 < nk) ? kc + 1 : 0;
+          if (kc + 1 < nk || pass + 1 < npass) load_chunk(kn, e_nxt, p_nxt);
+          const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
+          mbar_wait(a_empty + 8 * s, ph ^ 1);
+          const uint32_t stage = a_ring + s * kBytesA;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float h0 = tanh_approx(e_cur[i].x + p_cur[j].x);
+              const float h1 = tanh_approx(e_cur[i].y + p_cur[j].y);
+              const int r = rg * 16 + i * 8 + j;
+              const uint32_t addr = stage + r * 128 + ((((uint32_t)kp >> 2) ^ (uint32_t)j) << 4) + ((kp & 3) << 2);
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16x2(h0, h1)) : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * s);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) e_cur[i] = e_nxt[i];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p_cur[j] = p_nxt[j];
+        }
+      }
+    }
+  } else if (warp == kStoreWarp) {
+    // ===================================================================== hidden-ring store (G mode)
+    if (MODE == 1 && lane == 0) {
+      uint32_t it = 0;
+      for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        const int ring_row0 = (tile - p.tile_begin) * kTileM;
+        for (int pass = 0; pass < npass; ++pass) {
+          for (int kc = 0; kc < nk; ++kc, ++it) {
+            const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
+            mbar_wait(a_full + 8 * s, ph);
+            if (pass == 0) {
+              tma_store_2d(&tmHr, a_ring + s * kBytesA, kc * kBK, ring_row0);
+              tma_store_commit();
+              tma_store_wait_read<0>();
+            }
+            mbar_arrive(a_empty + 8 * s);
+          }
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
+                      const JointArgs& args, int grid, cudaStream_t stream) {
+  const size_t smem = joint_gemm_smem_bytes();
+  if (mode == 0) {
+    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    joint_gemm_kernel<0><<<grid, kNumThreads, smem, stream>>>(tmW, tmG, tmHr, args);
+  } else {
+    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    joint_gemm_kernel<1><<<grid, kNumThreads, smem, stream>>>(tmW, tmG, tmHr, args);
+  }
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rb

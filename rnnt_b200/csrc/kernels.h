@@ -1,0 +1,80 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "host_util.h"
+
+namespace rb {
+
+struct JointArgs {
+  const float* enc;       // (B,T,H) fp32, H contiguous
+  long long enc_sb, enc_st;
+  const float* pred;      // (B,U1,H) fp32, H contiguous
+  long long pred_sb, pred_su;
+  const float* bias2;     // [Vp] bias * log2(e); padding columns hold -1e30
+  const int* targets;     // (B,U) int32
+  int tgt_ld;
+  const int* T_len;
+  const int* U_len;
+  const int* tile_off;    // [B+1] prefix sum of tiles per utterance; tile_off[B] = total
+  int B, T, U1, H, Hp, V, Vp, blank;
+  int tile_begin, tile_cap;   // process tiles [tile_begin, min(total, tile_begin + tile_cap))
+  float* lp;              // F: (B,T,U1,2) log-probs (blank, label)
+  float* lse;             // F: (B,T,U1) log-sum-exp of the logits (natural log)
+  const float4* coef;     // G: (B,T,U1) (gamma*dc, eB*dc, eE*dc, lse)
+  const float* dcost;     // G: (B) or nullptr (only used to scale the clamp bound)
+  float clamp;            // G: <= 0 disables (torchaudio's clamp argument, rnnt/model.py:40 passes -1)
+};
+
+struct DhArgs {
+  const __nv_bfloat16* h_ring;   // [ring_rows, Hp] tanh activations of the chunk (G mode output)
+  const int* T_len;
+  const int* U_len;
+  const int* tile_off;
+  int B, T, U1, H, Hp, Vp;
+  int tile_begin, tile_cap;
+  float* d_enc;          // (B,T,H) fp32, accumulated with atomics (caller zero-fills)
+  float* d_pred;         // (B,U1,H)
+  float* dbg_dh;         // optional [ring_rows, Hp] fp32 raw dh dump (tests), or nullptr
+};
+
+struct DwArgs {
+  const int* tile_off;
+  int B, H, Hp, V, Vp;
+  int tile_begin, tile_cap;
+  float* dW;             // (V,H) fp32, accumulated with atomics (caller zero-fills)
+  int ksplit;
+};
+
+size_t joint_gemm_smem_bytes();
+int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
+                      const JointArgs& args, int grid, cudaStream_t stream);
+int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, int grid,
+                   cudaStream_t stream);
+int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream);
+
+// prep / small kernels (prep.cu, lattice.cu, decode.cu)
+int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
+                      cudaStream_t stream);
+int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __nv_bfloat16* Wb,
+                           float* bias2, cudaStream_t stream);
+int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, int T, int U1, float* alpha,
+                   float* beta, float* costs, cudaStream_t stream);
+int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
+                const int* T_len, const int* U_len, int B, int T, int U1, float4* coef, cudaStream_t stream);
+int launch_db(const __nv_bfloat16* g_ring, const int* tile_off, int B, int tile_begin, int tile_cap, int V, int Vp,
+              float* db, cudaStream_t stream);
+int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
+                          int B, int T, int U1, int V, int blank, float* lp, float* lse, cudaStream_t stream);
+int launch_dense_grads(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
+                       const float4* coef, int B, int T, int U1, int V, int blank, float clamp, float* grads,
+                       cudaStream_t stream);
+int launch_joint_argmax(const float* enc_rows, long long enc_stride, const float* pred_rows, long long pred_stride,
+                        const float* W, const float* bias, int N, int H, int V, int* tokens, float* top2,
+                        float* scratch, cudaStream_t stream);
+size_t joint_argmax_scratch_bytes(int N, int V);
+
+}  // namespace rb

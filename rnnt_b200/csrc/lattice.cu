@@ -1,0 +1,278 @@
+// Small kernels around the GEMMs: tile table, weight conversion, alpha/beta lattice, gradient coefficients,
+// and the dense-logits variants of the loss front/back end (for callers that already hold logits).
+//
+// Lattice = torchaudio ComputeAlphasBetasCosts (reference call site rnnt/model.py:35-41):
+//   alpha[0,0]=0; alpha[t,u]=LSE(alpha[t-1,u]+lpB[t-1,u], alpha[t,u-1]+lpE[t,u-1])
+//   beta[Tb-1,Ub]=lpB[Tb-1,Ub]; beta[t,u]=LSE(beta[t+1,u]+lpB[t,u], beta[t,u+1]+lpE[t,u]); cost=-beta[0,0]
+// One CTA per (utterance, direction); thread u walks anti-diagonals n = t+u.  The neighbour value crosses
+// threads through a double-buffered shared array (one __syncthreads per diagonal, no global spin-waits),
+// and the log-probs of the next 8 diagonals are prefetched into registers while the current 8 are consumed.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rb {
+namespace {
+
+__global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __restrict__ U_len, int B, int T, int U1,
+                                  int* __restrict__ tile_off, int* __restrict__ err_flag) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int acc = 0, bad = 0;
+  tile_off[0] = 0;
+  for (int b = 0; b < B; ++b) {
+    int Tb = T_len[b], Ub = U_len[b];
+    if (Tb < 1 || Tb > T || Ub < 0 || Ub > U1 - 1) bad = 1;
+    Tb = max(1, min(Tb, T));
+    Ub = max(0, min(Ub, U1 - 1));
+    acc += ((Tb + kTileT - 1) / kTileT) * ((Ub + 1 + kTileU - 1) / kTileU);
+    tile_off[b + 1] = acc;
+  }
+  if (err_flag) *err_flag = bad;
+}
+
+__global__ void convert_weights_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int H,
+                                       int Vp, int Hp, __nv_bfloat16* __restrict__ Wb, float* __restrict__ bias2) {
+  const long long n = static_cast<long long>(Vp) * Hp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i / Hp), k = static_cast<int>(i % Hp);
+    const float x = (v < V && k < H) ? W[static_cast<long long>(v) * H + k] : 0.f;
+    Wb[i] = __float2bfloat16_rn(x);
+    if (k == 0) bias2[v] = (v < V) ? bias[v] * kLog2e : -1e30f;
+  }
+}
+
+__device__ __forceinline__ float lse2f(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + log1pf(expf(fminf(a, b) - m));
+}
+
+constexpr int kPre = 8;
+
+__global__ void lattice_kernel(const float* __restrict__ lp, const int* __restrict__ T_len,
+                               const int* __restrict__ U_len, int T, int U1, float* __restrict__ alpha,
+                               float* __restrict__ beta, float* __restrict__ costs) {
+  extern __shared__ float sh[];   // 2 x (blockDim.x + 2)
+  const int b = blockIdx.x;
+  const bool is_beta = blockIdx.y == 1;
+  const int u = threadIdx.x;
+  const int Tb = max(1, min(T_len[b], T)), Ub = max(0, min(U_len[b], U1 - 1));
+  const int ndiag = Tb + Ub;
+  const int stride = blockDim.x + 2;
+  float* sh0 = sh + 1;             // sh0[-1] and sh0[blockDim.x] are -inf guards
+  float* sh1 = sh + stride + 1;
+  if (u == 0) {
+    sh0[-1] = -INFINITY; sh1[-1] = -INFINITY;
+    sh0[blockDim.x] = -INFINITY; sh1[blockDim.x] = -INFINITY;
+  }
+  sh0[u] = -INFINITY;
+  sh1[u] = -INFINITY;
+  __syncthreads();
+  const float2* lp2 = reinterpret_cast<const float2*>(lp) + static_cast<long long>(b) * T * U1;
+  float* out = (is_beta ? beta : alpha) + static_cast<long long>(b) * T * U1;
+  const bool col_ok = u <= Ub;
+
+  float2 cur[kPre], nxt[kPre];
+  auto fetch = [&](int g, float2 (&dst)[kPre]) {
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+      const int s = g * kPre + i;                       // step index 0..ndiag-1
+      const int n = is_beta ? (ndiag - 1 - s) : s;      // diagonal
+      const int t = n - u;
+      dst[i] = (s < ndiag && col_ok && t >= 0 && t < Tb) ? __ldg(lp2 + static_cast<long long>(t) * U1 + u)
+                                                          : make_float2(0.f, 0.f);
+    }
+  };
+  const int ngroups = (ndiag + kPre - 1) / kPre;
+  fetch(0, cur);
+  float own = -INFINITY;   // alpha: alpha(t-1,u)+lpB(t-1,u);  beta: beta(t+1,u)
+  for (int g = 0; g < ngroups; ++g) {
+    if (g + 1 < ngroups) fetch(g + 1, nxt);
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+      const int s = g * kPre + i;
+      if (s < ndiag) {    // uniform over the block
+        const int n = is_beta ? (ndiag - 1 - s) : s;
+        const int t = n - u;
+        float* wr = (s & 1) ? sh1 : sh0;
+        const float* rd = (s & 1) ? sh0 : sh1;
+        if (col_ok && t >= 0 && t < Tb) {
+          const float lpB = cur[i].x, lpE = cur[i].y;
+          float val;
+          if (!is_beta) {
+            if (n == 0) val = 0.f;
+            else val = lse2f(t > 0 ? own : -INFINITY, u > 0 ? rd[u - 1] : -INFINITY);
+            own = val + lpB;                       // feeds alpha(t+1,u)
+            wr[u] = (u < Ub) ? val + lpE : -INFINITY;   // feeds alpha(t,u+1)
+          } else {
+            if (t == Tb - 1 && u == Ub) val = lpB;
+            else val = lse2f(t < Tb - 1 ? own + lpB : -INFINITY, u < Ub ? rd[u + 1] + lpE : -INFINITY);
+            own = val;
+            wr[u] = val;
+          }
+          out[static_cast<long long>(t) * U1 + u] = val;
+          if (is_beta && n == 0) costs[b] = -val;
+        } else {
+          wr[u] = -INFINITY;
+        }
+        __syncthreads();
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) cur[i] = nxt[i];
+  }
+}
+
+__global__ void coef_kernel(const float* __restrict__ lp, const float* __restrict__ lse,
+                            const float* __restrict__ alpha, const float* __restrict__ beta,
+                            const float* __restrict__ dcost, const int* __restrict__ T_len,
+                            const int* __restrict__ U_len, int B, int T, int U1, float4* __restrict__ coef) {
+  const long long n = static_cast<long long>(B) * T * U1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int u = static_cast<int>(i % U1);
+    const int t = static_cast<int>((i / U1) % T);
+    const int b = static_cast<int>(i / (static_cast<long long>(U1) * T));
+    const int Tb = max(1, min(T_len[b], T)), Ub = max(0, min(U_len[b], U1 - 1));
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < Tb && u <= Ub) {
+      const float dc = dcost ? dcost[b] : 1.f;
+      const float logZ = beta[static_cast<long long>(b) * T * U1];
+      const float c = alpha[i] - logZ;
+      const float2 l = reinterpret_cast<const float2*>(lp)[i];
+      o.x = expf(c + beta[i]) * dc;
+      if (t < Tb - 1) o.y = expf(c + l.x + beta[i + U1]) * dc;
+      else if (u == Ub) o.y = expf(c + l.x) * dc;
+      if (u < Ub) o.z = expf(c + l.y + beta[i + 1]) * dc;
+      o.w = lse[i];
+    }
+    coef[i] = o;
+  }
+}
+
+// ---- dense-logits front end: one warp per lattice cell (torchaudio ReduceMax2D/ReduceLogSumExp/ComputeLogProbs)
+__global__ void dense_logprobs_kernel(const float* __restrict__ logits, const int* __restrict__ targets, int tgt_ld,
+                                      const int* __restrict__ T_len, const int* __restrict__ U_len, int B, int T,
+                                      int U1, int V, int blank, float* __restrict__ lp, float* __restrict__ lse) {
+  const long long ncell = static_cast<long long>(B) * T * U1;
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long i = w0; i < ncell; i += nw) {
+    const int u = static_cast<int>(i % U1);
+    const int t = static_cast<int>((i / U1) % T);
+    const int b = static_cast<int>(i / (static_cast<long long>(U1) * T));
+    const int Tb = T_len[b], Ub = U_len[b];
+    if (t >= Tb || u > Ub) continue;
+    const float* row = logits + i * V;
+    float m = -INFINITY;
+    for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(row[v] - m);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const float l = m + logf(s);
+      lse[i] = l;
+      float2 o2;
+      o2.x = row[blank] - l;
+      o2.y = (u < Ub) ? row[targets[static_cast<long long>(b) * tgt_ld + u]] - l : 0.f;
+      reinterpret_cast<float2*>(lp)[i] = o2;
+    }
+  }
+}
+
+// ---- dense-logits back end (torchaudio ComputeGradients): grads fully overwritten, zeros on padding
+__global__ void dense_grads_kernel(const float* __restrict__ logits, const int* __restrict__ targets, int tgt_ld,
+                                   const int* __restrict__ T_len, const int* __restrict__ U_len,
+                                   const float4* __restrict__ coef, int B, int T, int U1, int V, int blank,
+                                   float clamp, float* __restrict__ grads) {
+  const long long ncell = static_cast<long long>(B) * T * U1;
+  const int lane = threadIdx.x & 31;
+  const long long w0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long i = w0; i < ncell; i += nw) {
+    const int u = static_cast<int>(i % U1);
+    const int t = static_cast<int>((i / U1) % T);
+    const int b = static_cast<int>(i / (static_cast<long long>(U1) * T));
+    const int Tb = T_len[b], Ub = U_len[b];
+    float* out = grads + i * V;
+    if (t >= Tb || u > Ub) {
+      for (int v = lane; v < V; v += 32) out[v] = 0.f;
+      continue;
+    }
+    const float4 c = coef[i];
+    const int tgt = (u < Ub) ? targets[static_cast<long long>(b) * tgt_ld + u] : -1;
+    const float* row = logits + i * V;
+    for (int v = lane; v < V; v += 32) {
+      float g = expf(row[v] - c.w) * c.x;
+      if (v == blank) g -= c.y;
+      if (v == tgt) g -= c.z;
+      if (clamp > 0.f) g = fminf(fmaxf(g, -clamp), clamp);
+      out[v] = g;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
+                      cudaStream_t stream) {
+  tile_table_kernel<<<1, 32, 0, stream>>>(T_len, U_len, B, T, U1, tile_off, err_flag);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __nv_bfloat16* Wb,
+                           float* bias2, cudaStream_t stream) {
+  const long long n = static_cast<long long>(Vp) * Hp;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 4096));
+  convert_weights_kernel<<<grid, 256, 0, stream>>>(W, bias, V, H, Vp, Hp, Wb, bias2);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, int T, int U1, float* alpha,
+                   float* beta, float* costs, cudaStream_t stream) {
+  const int threads = ((U1 + 31) / 32) * 32;
+  RB_REQUIRE(threads <= 1024, -5, "lattice kernel supports U+1 <= 1024 (got %d)", U1);
+  const size_t smem = 2 * (threads + 2) * sizeof(float);
+  lattice_kernel<<<dim3(B, 2), threads, smem, stream>>>(lp, T_len, U_len, T, U1, alpha, beta, costs);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
+                const int* T_len, const int* U_len, int B, int T, int U1, float4* coef, cudaStream_t stream) {
+  const long long n = static_cast<long long>(B) * T * U1;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8));
+  coef_kernel<<<grid, 256, 0, stream>>>(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
+                          int B, int T, int U1, int V, int blank, float* lp, float* lse, cudaStream_t stream) {
+  const long long ncell = static_cast<long long>(B) * T * U1;
+  const int grid = static_cast<int>(std::min<long long>((ncell + 7) / 8, 148 * 16));
+  dense_logprobs_kernel<<<grid, 256, 0, stream>>>(logits, targets, tgt_ld, T_len, U_len, B, T, U1, V, blank, lp, lse);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_dense_grads(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
+                       const float4* coef, int B, int T, int U1, int V, int blank, float clamp, float* grads,
+                       cudaStream_t stream) {
+  const long long ncell = static_cast<long long>(B) * T * U1;
+  const int grid = static_cast<int>(std::min<long long>((ncell + 7) / 8, 148 * 16));
+  dense_grads_kernel<<<grid, 256, 0, stream>>>(logits, targets, tgt_ld, T_len, U_len, coef, B, T, U1, V, blank,
+                                               clamp, grads);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rb

@@ -1,0 +1,274 @@
+"""Host-side mirror of the reference's loss call (rnnt/model.py:35-41) on top of the C-ABI.
+
+`joint_rnnt_loss` is the fused entry (joint + loss, no logits tensor); `rnnt_loss` has the exact signature of
+`torchaudio.functional.rnnt_loss` and accepts either dense logits or the lazy handle `JointNetwork.forward`
+returns in zero-edit mode.  PyTorch is used for device memory, streams and autograd plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(1 << 30)))
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("rnnt_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def _validate_lengths(T, U1, logit_lengths, target_lengths):
+    """Same checks (and messages) torchaudio's rnnt_loss raises.  Synchronises."""
+    if int(logit_lengths.max()) != T:
+        raise RuntimeError("input length mismatch")
+    if int(target_lengths.max()) + 1 != U1:
+        raise RuntimeError("output length mismatch")
+
+
+def _check_index_tensors(targets, logit_lengths, target_lengths):
+    if targets.dtype != torch.int32:
+        raise RuntimeError("targets must be int32 type")
+    if logit_lengths.dtype != torch.int32:
+        raise RuntimeError("logit_lengths must be int32 type")
+    if target_lengths.dtype != torch.int32:
+        raise RuntimeError("target_lengths must be int32 type")
+    if not targets.is_contiguous():
+        raise RuntimeError("targets must be contiguous")
+
+
+def pick_ring_tiles(B: int, T: int, U1: int, H: int, V: int, ring_bytes: Optional[int] = None) -> int:
+    """Tiles per backward chunk: the batch's tile bound split into equal chunks of at most `ring_bytes`."""
+    ring_bytes = _DEFAULT_RING_BYTES if ring_bytes is None else ring_bytes
+    max_tiles = int(_lib.lib().rnnt_b200_max_tiles(B, T, U1))
+    hp = (H + 63) // 64 * 64
+    vp = (V + 255) // 256 * 256
+    per_tile = 128 * (hp + vp) * 2
+    cap = max(1, ring_bytes // per_tile)
+    nchunks = (max_tiles + cap - 1) // cap
+    return (max_tiles + nchunks - 1) // nchunks
+
+
+def workspace_bytes(B, T, U1, H, V, ring_tiles):
+    fwd, bwd = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(_lib.lib().rnnt_b200_workspace_bytes(B, T, U1, H, V, ring_tiles, C.byref(fwd), C.byref(bwd)),
+               "workspace_bytes")
+    return fwd.value, bwd.value
+
+
+class _FusedJointLoss(torch.autograd.Function):
+    """costs[B] = transducer loss of joint_ln(tanh(enc + pred)); residuals are 5 lattice-sized fp32 tensors."""
+
+    @staticmethod
+    def forward(ctx, enc, pred, weight, bias, targets, logit_lengths, target_lengths, blank, clamp, ring_bytes):
+        L = _lib.lib()
+        B, T, H = enc.shape
+        U1 = pred.shape[1]
+        V = weight.shape[0]
+        dev = enc.device
+        enc_c = enc if enc.stride(2) == 1 and enc.stride(1) % 2 == 0 and enc.stride(0) % 2 == 0 else enc.contiguous()
+        pred_c = pred.contiguous()
+        weight_c = weight.contiguous()
+        bias_c = bias.contiguous()
+        costs = torch.empty(B, dtype=torch.float32, device=dev)
+        lp = torch.empty(B, T, U1, 2, dtype=torch.float32, device=dev)
+        lse = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
+        alpha = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
+        beta = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
+        fwd_bytes, _ = workspace_bytes(B, T, U1, H, V, 0)
+        ws = torch.empty(fwd_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.rnnt_b200_joint_loss_fwd(
+                enc_c.data_ptr(), enc_c.stride(0), enc_c.stride(1), pred_c.data_ptr(), weight_c.data_ptr(),
+                bias_c.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
+                B, T, U1, H, V, blank, costs.data_ptr(), lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(),
+                beta.data_ptr(), None, ws.data_ptr(), fwd_bytes, _stream_ptr(dev)), "joint_loss_fwd")
+        ctx.save_for_backward(enc_c, pred_c, weight_c, bias_c, targets, logit_lengths, target_lengths,
+                              lp, lse, alpha, beta)
+        ctx.blank, ctx.clamp, ctx.ring_bytes = blank, clamp, ring_bytes
+        ctx.mark_non_differentiable(lp, lse, alpha, beta)
+        return costs, lp, lse, alpha, beta
+
+    @staticmethod
+    def backward(ctx, dcost, *_unused):
+        L = _lib.lib()
+        enc, pred, weight, bias, targets, logit_lengths, target_lengths, lp, lse, alpha, beta = ctx.saved_tensors
+        B, T, H = enc.shape
+        U1 = pred.shape[1]
+        V = weight.shape[0]
+        dev = enc.device
+        dcost = dcost.contiguous().float()
+        d_enc = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        d_pred = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
+        dW = torch.empty(V, H, dtype=torch.float32, device=dev)
+        db = torch.empty(V, dtype=torch.float32, device=dev)
+        ring_tiles = pick_ring_tiles(B, T, U1, H, V, ctx.ring_bytes)
+        _, bwd_bytes = workspace_bytes(B, T, U1, H, V, ring_tiles)
+        ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.rnnt_b200_joint_loss_bwd(
+                enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(), B, T, U1, H, V, ctx.blank,
+                lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(), dcost.data_ptr(),
+                float(ctx.clamp), d_enc.data_ptr(), d_pred.data_ptr(), dW.data_ptr(), db.data_ptr(), ring_tiles,
+                ws.data_ptr(), bwd_bytes, _stream_ptr(dev)), "joint_loss_bwd")
+        ctx.last_workspace = ws   # kept alive for tests that inspect the rings
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None
+
+
+def _reduce(costs, reduction):
+    if reduction == "none":
+        return costs
+    if reduction == "mean":
+        return costs.mean()
+    if reduction == "sum":
+        return costs.sum()
+    raise ValueError('reduction should be one of "none", "mean", "sum"')
+
+
+def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths, blank: int = -1,
+                    clamp: float = -1, reduction: str = "mean", validate: bool = True,
+                    ring_bytes: Optional[int] = None, return_residuals: bool = False):
+    """Fused replacement for `joint_ln(tanh(a.unsqueeze(2) + p.unsqueeze(1)))` (rnnt/joint.py:32-39) followed by
+    `torchaudio.functional.rnnt_loss(..., blank, clamp, reduction)` (rnnt/model.py:35-41).
+
+    audio_frame (B,T,H) and text_frame (B,U+1,H) are the (already projected) joint inputs; weight (V,H) / bias (V)
+    are joint_ln's parameters.  Per-utterance costs when reduction="none".  validate=True performs torchaudio's
+    host-side length checks (one device sync, as the reference does); pass False on the hot loop.
+    """
+    _require_cuda(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths)
+    if audio_frame.dtype != torch.float32 or text_frame.dtype != torch.float32:
+        raise RuntimeError("joint inputs must be float32 (the fused kernels convert to bf16 internally)")
+    if audio_frame.dim() != 3 or text_frame.dim() != 3 or audio_frame.shape[0] != text_frame.shape[0] \
+            or audio_frame.shape[2] != text_frame.shape[2] or weight.shape[1] != audio_frame.shape[2]:
+        raise RuntimeError("expected audio (B,T,H), text (B,U+1,H) and weight (V,H)")
+    _check_index_tensors(targets, logit_lengths, target_lengths)
+    if targets.shape[0] != audio_frame.shape[0] or targets.shape[1] != text_frame.shape[1] - 1:
+        raise RuntimeError("output length mismatch")
+    if validate:
+        _validate_lengths(audio_frame.shape[1], text_frame.shape[1], logit_lengths, target_lengths)
+    costs, lp, lse, alpha, beta = _FusedJointLoss.apply(audio_frame, text_frame, weight.float(), bias.float(),
+                                                        targets, logit_lengths, target_lengths, int(blank),
+                                                        float(clamp), ring_bytes)
+    out = _reduce(costs, reduction)
+    if return_residuals:
+        return out, dict(lp=lp, lse=lse, alpha=alpha, beta=beta)
+    return out
+
+
+class _DenseLoss(torch.autograd.Function):
+    """torchaudio.functional.rnnt_loss on materialised logits: log-softmax gather, lattice, gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, logit_lengths, target_lengths, blank, clamp):
+        L = _lib.lib()
+        B, T, U1, V = logits.shape
+        dev = logits.device
+        costs = torch.empty(B, dtype=torch.float32, device=dev)
+        lp = torch.empty(B, T, U1, 2, dtype=torch.float32, device=dev)
+        lse = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
+        alpha = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
+        beta = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.rnnt_b200_loss_dense_fwd(
+                logits.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
+                B, T, U1, V, blank, costs.data_ptr(), lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(),
+                beta.data_ptr(), _stream_ptr(dev)), "loss_dense_fwd")
+        ctx.save_for_backward(logits, targets, logit_lengths, target_lengths, lp, lse, alpha, beta)
+        ctx.blank, ctx.clamp = blank, clamp
+        return costs
+
+    @staticmethod
+    def backward(ctx, dcost):
+        L = _lib.lib()
+        logits, targets, logit_lengths, target_lengths, lp, lse, alpha, beta = ctx.saved_tensors
+        B, T, U1, V = logits.shape
+        dev = logits.device
+        grads = torch.empty_like(logits)
+        coef = torch.empty(B, T, U1, 4, dtype=torch.float32, device=dev)
+        dcost = dcost.contiguous().float()
+        clamped = ctx.clamp > 0
+        with torch.cuda.device(dev):
+            _lib.check(L.rnnt_b200_loss_dense_bwd(
+                logits.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
+                B, T, U1, V, ctx.blank, lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                None if clamped else dcost.data_ptr(), float(ctx.clamp), coef.data_ptr(), grads.data_ptr(),
+                _stream_ptr(dev)), "loss_dense_bwd")
+        if clamped:
+            grads = grads * dcost.view(-1, 1, 1, 1)
+        return grads, None, None, None, None, None
+
+
+def rnnt_loss(logits, targets, logit_lengths, target_lengths, blank: int = -1, clamp: float = -1,
+              reduction: str = "mean", fused_log_softmax: bool = True):
+    """Same signature and error behaviour as torchaudio.functional.rnnt_loss (call site rnnt/model.py:35-41).
+
+    `logits` may be the lazy handle a zero-edit-mode JointNetwork returns; the call then runs the fused kernels and
+    no (B,T,U+1,V) tensor is ever created.  Dense fp32 logits run the dense CUDA kernels.
+    """
+    from .joint import LazyJointLogits
+    if isinstance(logits, LazyJointLogits):
+        return joint_rnnt_loss(logits.audio, logits.text, logits.weight, logits.bias, targets, logit_lengths,
+                               target_lengths, blank=blank, clamp=clamp, reduction=reduction)
+    if not fused_log_softmax:
+        raise RuntimeError("rnnt_b200.rnnt_loss only implements fused_log_softmax=True (what the reference uses)")
+    _require_cuda(logits, targets, logit_lengths, target_lengths)
+    if logits.dtype != torch.float32:
+        raise RuntimeError("logits must be float32 or float16 (half) type" if logits.dtype not in
+                           (torch.float16,) else "rnnt_b200 dense loss supports float32 logits only")
+    if not logits.is_contiguous():
+        raise RuntimeError("logits must be contiguous")
+    if logits.dim() != 4:
+        raise RuntimeError("logits must be 4-D (batch, time, target, class)")
+    _check_index_tensors(targets, logit_lengths, target_lengths)
+    _validate_lengths(logits.shape[1], logits.shape[2], logit_lengths, target_lengths)
+    costs = _DenseLoss.apply(logits, targets, logit_lengths, target_lengths, int(blank), float(clamp))
+    return _reduce(costs, reduction)
+
+
+def lattice(lp, logit_lengths, target_lengths):
+    """alpha, beta, costs from log-probs (B,T,U+1,2) -- the lattice kernel alone."""
+    _require_cuda(lp, logit_lengths, target_lengths)
+    B, T, U1, _ = lp.shape
+    lp = lp.contiguous().float()
+    alpha = torch.full((B, T, U1), float("-inf"), dtype=torch.float32, device=lp.device)
+    beta = torch.full((B, T, U1), float("-inf"), dtype=torch.float32, device=lp.device)
+    costs = torch.empty(B, dtype=torch.float32, device=lp.device)
+    with torch.cuda.device(lp.device):
+        _lib.check(_lib.lib().rnnt_b200_lattice(lp.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
+                                                B, T, U1, alpha.data_ptr(), beta.data_ptr(), costs.data_ptr(),
+                                                _stream_ptr(lp.device)), "lattice")
+    return alpha, beta, costs
+
+
+def joint_argmax(audio_rows, text_rows, weight, bias, return_margin: bool = False):
+    """tokens[n] = argmax(joint.single_forward(audio_rows[n], text_rows[n])) in fp32 (rnnt/model.py:110-113)."""
+    _require_cuda(audio_rows, text_rows, weight, bias)
+    N, H = audio_rows.shape
+    V = weight.shape[0]
+    if audio_rows.stride(1) != 1:
+        audio_rows = audio_rows.contiguous()
+    if text_rows.stride(1) != 1:
+        text_rows = text_rows.contiguous()
+    weight = weight.contiguous()
+    bias = bias.contiguous()
+    dev = audio_rows.device
+    tokens = torch.empty(N, dtype=torch.int32, device=dev)
+    margin = torch.empty(N, dtype=torch.float32, device=dev) if return_margin else None
+    L = _lib.lib()
+    scratch = torch.empty(max(1, L.rnnt_b200_joint_argmax_scratch_bytes(N, V)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.rnnt_b200_joint_argmax(
+            audio_rows.data_ptr(), audio_rows.stride(0), text_rows.data_ptr(), text_rows.stride(0),
+            weight.data_ptr(), bias.data_ptr(), N, H, V, tokens.data_ptr(),
+            margin.data_ptr() if return_margin else None, scratch.data_ptr(), _stream_ptr(dev)), "joint_argmax")
+    return (tokens, margin) if return_margin else tokens

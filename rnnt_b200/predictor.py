@@ -1,0 +1,58 @@
+"""Host-side mirror of the reference's ConvPredictor (rnnt/predictor.py:189-229, rnnt/causalconv.py:9-39).
+
+Not a kernel target of this round: its output is an input of the hot path.  It exists so that the
+drop-in RNNTModel and the batched greedy decode can be built and tested without the reference tree; parameter names
+match the reference's state_dict.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+class CausalConv1d(torch.nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, dilation, additional_context: int = 0):
+        super().__init__()
+        self.conv = torch.nn.Conv1d(in_channels, out_channels, kernel_size, stride, dilation=dilation)
+        self.padding = (kernel_size - 1) * dilation - stride + 1
+        if additional_context < 0:
+            raise ValueError("additional_context must be non-negative")
+        if additional_context > self.padding:
+            raise ValueError("additional_context can't be greater than the padding")
+        self.additional_context = additional_context
+        self.left_padding = self.padding - additional_context
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (self.left_padding, 0)))
+
+
+class ConvPredictor(torch.nn.Module):
+    RECEPTIVE_FIELD = 7   # 1 + (3-1) + (5-1) tokens
+
+    def __init__(self, num_symbols: int, output_dim: int, symbol_embedding_dim: int, dropout: float) -> None:
+        super().__init__()
+        self.embedding = torch.nn.Embedding(num_symbols, symbol_embedding_dim)
+        self.input_layer_norm = torch.nn.LayerNorm(symbol_embedding_dim)
+        self.conv1 = CausalConv1d(symbol_embedding_dim, symbol_embedding_dim, kernel_size=3, stride=1, dilation=1)
+        self.conv2 = CausalConv1d(symbol_embedding_dim, symbol_embedding_dim, kernel_size=5, stride=1, dilation=1)
+        self.linear = torch.nn.Linear(symbol_embedding_dim, output_dim)
+        self.output_layer_norm = torch.nn.LayerNorm(output_dim)
+        self.dropout = torch.nn.Dropout(p=dropout)
+
+    def forward(self, input):
+        x = self.embedding(input)
+        x = self.input_layer_norm(x)
+        x = x.permute(0, 2, 1)
+        x = self.dropout(F.gelu(self.conv1(x)))
+        x = self.dropout(F.gelu(self.conv2(x)))
+        x = x.permute(0, 2, 1)
+        return self.output_layer_norm(self.linear(x))
+
+    @torch.no_grad()
+    def last_step(self, windows):
+        """Predictor output for the LAST position of each row of `windows` (N, L<=7 or exactly 7 tokens).
+
+        The output at position i depends only on tokens i-6..i, so a 7-token window reproduces what the reference's
+        full-history re-run (rnnt/model.py:122-123) yields at the last position; shorter histories are passed
+        whole so the left zero padding matches."""
+        return self.forward(windows)[:, -1, :]

@@ -1,0 +1,117 @@
+"""Shared helpers for the GPU parity tests: input generation, direct C-ABI calls, ring <-> lattice mapping."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+
+def make_inputs(B, T, U, H, V, seed=1234, ragged=False, device="cuda", scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    enc = torch.randn(B, H, T, generator=g).permute(0, 2, 1).contiguous() * scale   # dense copy of the model.py:28 view
+    pred = torch.randn(B, U + 1, H, generator=g) * scale
+    bound = 1.0 / (H ** 0.5)
+    W = (torch.rand(V, H, generator=g) * 2 - 1) * bound       # nn.Linear default init range (joint.py:18)
+    b = (torch.rand(V, generator=g) * 2 - 1) * bound
+    targets = torch.randint(0, V - 1, (B, U), generator=g, dtype=torch.int32)
+    if ragged:
+        T_len = torch.randint(max(1, T // 2), T + 1, (B,), generator=g, dtype=torch.int32)
+        U_len = torch.randint(U // 2, U + 1, (B,), generator=g, dtype=torch.int32)
+        T_len[0] = T
+        U_len[B - 1] = U
+    else:
+        T_len = torch.full((B,), T, dtype=torch.int32)
+        U_len = torch.full((B,), U, dtype=torch.int32)
+    to = lambda x: x.to(device)
+    return dict(enc=to(enc), pred=to(pred), W=to(W), b=to(b), targets=to(targets), T_len=to(T_len), U_len=to(U_len))
+
+
+def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0):
+    """Call the C-ABI forward + backward directly; returns outputs plus the raw workspace and its layout."""
+    from rnnt_b200 import _lib
+    from rnnt_b200.functional import _stream_ptr, pick_ring_tiles
+    L = _lib.lib()
+    enc, pred, W, b = inp["enc"], inp["pred"], inp["W"], inp["b"]
+    targets, T_len, U_len = inp["targets"], inp["T_len"], inp["U_len"]
+    B, T, H = enc.shape
+    U1 = pred.shape[1]
+    V = W.shape[0]
+    dev = enc.device
+    if ring_tiles is None:
+        ring_tiles = pick_ring_tiles(B, T, U1, H, V)
+    offs = (C.c_int64 * 8)()
+    hp, vp = C.c_int(0), C.c_int(0)
+    _lib.check(L.rnnt_b200_debug_ws_layout(B, T, U1, H, V, ring_tiles, offs, C.byref(hp), C.byref(vp)), "layout")
+    ws = torch.zeros(int(offs[6]), dtype=torch.uint8, device=dev)
+    f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+    out = dict(costs=f(B), lp=f(B, T, U1, 2), lse=f(B, T, U1), alpha=f(B, T, U1), beta=f(B, T, U1),
+               d_enc=f(B, T, H), d_pred=f(B, U1, H), dW=f(V, H), db=f(V))
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = _stream_ptr(dev)
+    _lib.check(L.rnnt_b200_joint_loss_fwd(
+        enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
+        targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["costs"].data_ptr(),
+        out["lp"].data_ptr(), out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(),
+        status.data_ptr(), ws.data_ptr(), ws.numel(), st), "fwd")
+    torch.cuda.synchronize()
+    if dcost is None:
+        dcost = torch.ones(B, dtype=torch.float32, device=dev)
+    _lib.check(L.rnnt_b200_joint_loss_bwd(
+        enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
+        targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["lp"].data_ptr(),
+        out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(), dcost.data_ptr(), float(clamp),
+        out["d_enc"].data_ptr(), out["d_pred"].data_ptr(), out["dW"].data_ptr(), out["db"].data_ptr(),
+        ring_tiles, ws.data_ptr(), ws.numel(), st), "bwd")
+    torch.cuda.synchronize()
+    out.update(ws=ws, offs=[int(x) for x in offs], Hp=hp.value, Vp=vp.value, ring_tiles=ring_tiles,
+               status=int(status.item()))
+    return out
+
+
+def ring_views(out):
+    ws, offs, Hp, Vp = out["ws"], out["offs"], out["Hp"], out["Vp"]
+    rows = out["ring_tiles"] * 128
+    g = ws[offs[4]:offs[4] + rows * Vp * 2].view(torch.bfloat16).view(rows, Vp)
+    h = ws[offs[5]:offs[5] + rows * Hp * 2].view(torch.bfloat16).view(rows, Hp)
+    return g, h
+
+
+def tile_rows(T_len, U_len):
+    """For every ring row of the (single-chunk) backward: (b, t, u, valid).  Mirrors the kernels' tile map."""
+    rows = []
+    for b, (Tb, Ub) in enumerate(zip(T_len.tolist(), U_len.tolist())):
+        nt, nu = (Tb + 15) // 16, (Ub + 1 + 7) // 8
+        for it in range(nt):
+            for iu in range(nu):
+                for r in range(128):
+                    t, u = it * 16 + (r >> 3), iu * 8 + (r & 7)
+                    rows.append((b, t, u, t < Tb and u <= Ub))
+    return rows
+
+
+def torch_reference(inp, emulate_bf16=False, dcost=None):
+    """fp32 torch restatement on the SAME device (oracle/ref_path.py semantics), optionally with bf16-rounded
+    GEMM operands to separate kernel bugs from precision."""
+    import torchaudio
+    enc = inp["enc"].detach().clone().requires_grad_(True)
+    pred = inp["pred"].detach().clone().requires_grad_(True)
+    W = inp["W"].detach().clone().requires_grad_(True)
+    b = inp["b"].detach().clone().requires_grad_(True)
+    h = torch.tanh(enc.unsqueeze(2) + pred.unsqueeze(1))
+    if emulate_bf16:
+        h = h + (h.detach().bfloat16().float() - h.detach())
+        Wq = W + (W.detach().bfloat16().float() - W.detach())
+    else:
+        Wq = W
+    logits = torch.nn.functional.linear(h, Wq, b)
+    costs = torchaudio.functional.rnnt_loss(logits, inp["targets"], inp["T_len"], inp["U_len"], blank=-1, clamp=-1,
+                                            reduction="none")
+    costs.backward(torch.ones_like(costs) if dcost is None else dcost)
+    return dict(costs=costs.detach(), d_enc=enc.grad, d_pred=pred.grad, dW=W.grad, db=b.grad,
+                logits=logits.detach())
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / max(b.norm(), 1e-30)), float((a - b).abs().max())
