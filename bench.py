@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the RNN-T joint + transducer-loss hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one fused joint+loss forward AND backward over one synthetic batch (per GPU: B=32, T=400, U=100,
+H=1024, V=1024 -- BASELINE.json configs[1]); with N>1 (launched by torchrun, one rank per GPU) every rank
+processes its own B=32 utterances (global batch 32*N, no data-path collective) and the step ends with one NCCL
+all-reduce of the joint + predictor weight gradients (4,200,448 fp32).  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's own CPU implementation of the path (torch nn.functional.linear + tanh +
+torchaudio.functional.rnnt_loss forward+backward, i.e. rnnt/joint.py:25-39 + rnnt/model.py:35-41 restated in
+oracle/ref_path.py) on the box's host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RNN-T joint+loss fwd+bwd lattice-cells/s at B=32,T=400,U=100,V=1024"
+UNIT = "lattice-cells/s"
+B, T, U, H, V = 32, 400, 100, 1024, 1024
+PRED_GRAD_ELEMS = 3_150_848        # ConvPredictor parameters that ride the same all-reduce
+FLOP_PER_CELL_GEMM = 2 * H * V     # one H x V contraction per lattice cell
+CPU_SAMPLE = dict(B=2, T=400, U=100)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))),
+                    hbm=float(p.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(power),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def synth_inputs(torch, seed, device, b=B, t=T, u=U, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    enc = torch.randn(b, t, H, generator=g)
+    pred = torch.randn(b, u + 1, H, generator=g)
+    bound = 1.0 / (H ** 0.5)
+    W = (torch.rand(V, H, generator=g) * 2 - 1) * bound
+    bias = (torch.rand(V, generator=g) * 2 - 1) * bound
+    targets = torch.randint(0, V - 1, (b, u), generator=g, dtype=torch.int32)
+    T_len = torch.full((b,), t, dtype=torch.int32)
+    U_len = torch.full((b,), u, dtype=torch.int32)
+    d = dict(enc=enc, pred=pred, W=W, b=bias, targets=targets, T_len=T_len, U_len=U_len)
+    if pin:
+        return {k: v.pin_memory() for k, v in d.items()}
+    return {k: v.to(device) for k, v in d.items()}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(torch, inp):
+    from oracle.ref_path import ref_loss_and_grads
+    return ref_loss_and_grads(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"],
+                              inp["U_len"], reduction="mean")
+
+
+def time_cpu_reference(steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = synth_inputs(torch, 1234, "cpu", **{k.lower(): v for k, v in CPU_SAMPLE.items()})
+    cells = CPU_SAMPLE["B"] * CPU_SAMPLE["T"] * (CPU_SAMPLE["U"] + 1)
+    for _ in range(warmup):
+        cpu_reference_step(torch, inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(torch, inp)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return dict(value=cells / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"B={CPU_SAMPLE['B']},T={CPU_SAMPLE['T']},U={CPU_SAMPLE['U']},H={H},V={V} fp32, "
+                       f"torch {torch.__version__} linear+tanh + torchaudio rnnt_loss fwd+bwd, {steps} timed step(s) "
+                       f"of {cells} cells, {dt:.2f} s/step"), dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = max(1, min(args.warmup, 1))
+    base, dt = time_cpu_reference(steps, warmup)
+    line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"joint+loss fwd+bwd, bounded CPU sample {base['sample']}"),
+                cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from rnnt_b200 import _lib
+    from rnnt_b200.functional import joint_rnnt_loss
+    from rnnt_b200.parallel import GradAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    n_sets = 3   # rotating input sets: 3 x 70 MB > 126 MB L2, so inputs are L2-cold every step
+    sets = [synth_inputs(torch, 1234 + rank * 16 + i, dev) for i in range(n_sets)]
+    for s in sets:
+        for k in ("enc", "pred", "W", "b"):
+            s[k].requires_grad_(True)
+    pred_grad_stub = torch.zeros(PRED_GRAD_ELEMS, dtype=torch.float32, device=dev)
+    reducer = GradAllReducer([], average=True)
+
+    def step(s):
+        for k in ("enc", "pred", "W", "b"):
+            s[k].grad = None
+        loss = joint_rnnt_loss(s["enc"], s["pred"], s["W"], s["b"], s["targets"], s["T_len"], s["U_len"],
+                               blank=-1, clamp=-1, reduction="mean", validate=False)
+        loss.backward()
+        if world > 1:
+            reducer.all_reduce_grads([s["W"].grad, s["b"].grad, pred_grad_stub], wait=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(sets[i % n_sets])
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launch stream, clocks sampled, per-kernel events on
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.rnnt_b200_profile_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        last = step(sets[i % n_sets])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    fam_ms = (C.c_float * 8)()
+    fam_n = (C.c_int64 * 8)()
+    _lib.check(L.rnnt_b200_profile_end(fam_ms, fam_n), "profile_end")
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(last)
+
+    # ---- e2e: same step through the public API from pinned HOST buffers, result read back to host
+    host = synth_inputs(torch, 4321 + rank, dev, pin=True)
+    devbuf = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    for k in ("enc", "pred", "W", "b"):
+        devbuf[k].requires_grad_(True)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        with torch.no_grad():
+            for k, v in host.items():
+                devbuf[k].copy_(v, non_blocking=True)
+        loss = step(devbuf)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(host_loss)
+
+    for _ in range(min(2, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks
+    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        peaks = load_peaks()
+        cells_step = B * T * (U + 1) * world
+        ms_step = ms_total / args.steps
+        value = cells_step / (ms_step * 1e-3)
+        names = ["prep", "joint_gemm_fwd", "lattice", "joint_gemm_bwd", "dh_gemm", "dw_gemm", "db", "other"]
+        kern = {}
+        gemm_flops_per_step_rank = B * T * (U + 1) * FLOP_PER_CELL_GEMM
+        for i, nm in enumerate(names):
+            if fam_n[i] == 0:
+                continue
+            per_step_ms = fam_ms[i] / args.steps
+            kern[nm] = dict(ms_per_step=per_step_ms, launches_per_step=fam_n[i] / args.steps,
+                            share=per_step_ms / ms_step)
+            if nm in ("joint_gemm_fwd", "joint_gemm_bwd", "dh_gemm", "dw_gemm"):
+                kern[nm]["tflops"] = gemm_flops_per_step_rank / (per_step_ms * 1e-3) / 1e12
+        gemms = {k: v for k, v in kern.items() if "tflops" in v}
+        dom = max(gemms, key=lambda k: gemms[k]["ms_per_step"])
+        launches_dom = gemms[dom]["launches_per_step"]
+        achieved = gemms[dom]["tflops"]
+        roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
+                        frac=achieved / peaks["tflops"], traffic=None, peak_source=peaks["source"],
+                        flops_per_launch=gemm_flops_per_step_rank / launches_dom,
+                        avg_launch_ms=gemms[dom]["ms_per_step"] / launches_dom,
+                        whole_step_frac_credited=(value / world) * 3 * FLOP_PER_CELL_GEMM / (peaks["tflops"] * 1e12),
+                        kernels=kern)
+        cpu_base, _ = time_cpu_reference(1, 1) if world == 1 and not args.no_cpu_baseline else (None, None)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic",
+                    config=dict(workload=f"joint+loss fused fwd+bwd, per-GPU B={B},T={T},U={U},H={H},V={V} "
+                                         f"(BASELINE configs[1]); global batch {B * world}",
+                                parallelism=f"dp{world} by utterance, all-reduce of {V * H + V + PRED_GRAD_ELEMS} "
+                                            "fp32 grads" if world > 1 else "single GPU",
+                                l2="3 rotating input sets (210 MB > 126 MB L2) + ~16 GB/step ring traffic",
+                                loss=loss_val),
+                    clocks=clocks,
+                    e2e=dict(value=cells_step / (e2e_ms * 1e-3 / args.steps), unit=UNIT,
+                             h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
+                    gpu_launches=int(sum(fam_n)),
+                    roofline=roofline)
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

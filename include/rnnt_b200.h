@@ -85,6 +85,14 @@ int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const floa
                            const float* W, const float* bias, int N, int H, int V, int32_t* tokens, float* margin,
                            void* scratch, void* stream);
 
+/* Opt-in measurement hook (bench.py): between begin and end every kernel launch of the library is bracketed by
+ * CUDA events on its launch stream.  end() synchronises on those events and returns, per kernel family, the summed
+ * device time in ms and the number of launches.  HOST pointers.  Families: 0 prep (tile table, weight conversion,
+ * gradient coefficients), 1 joint GEMM forward, 2 lattice, 3 joint GEMM backward-recompute, 4 dh GEMM, 5 dW GEMM,
+ * 6 db, 7 other (dense-logits kernels, decode). */
+int rnnt_b200_profile_begin(void);
+int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
+
 /* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
  *   offsets[0] tile table (B+1 int32 prefix sums of tiles per utterance, then one status int)
  *   offsets[1] W as bf16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)

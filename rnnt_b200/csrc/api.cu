@@ -251,6 +251,14 @@ int rnnt_b200_loss_dense_bwd(const float* logits, const int32_t* targets, const 
   return rb::launch_dense_grads(logits, targets, U1 - 1, T_len, U_len, coef, B, T, U1, V, blank, clamp, grads, stream);
 }
 
+int rnnt_b200_profile_begin(void) { return rb::prof_begin(); }
+int rnnt_b200_profile_end(float* ms, int64_t* launches) {
+  long long l[rb::kProfFamilies];
+  const int rc = rb::prof_end(ms, l);
+  for (int i = 0; i < rb::kProfFamilies; ++i) launches[i] = l[i];
+  return rc;
+}
+
 size_t rnnt_b200_joint_argmax_scratch_bytes(int N, int V) { return rb::joint_argmax_scratch_bytes(N, V); }
 
 int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const float* pred_rows, int64_t pred_stride,

@@ -99,6 +99,7 @@ size_t joint_argmax_scratch_bytes(int N, int V) {
 int launch_joint_argmax(const float* enc_rows, long long enc_stride, const float* pred_rows, long long pred_stride,
                         const float* W, const float* bias, int N, int H, int V, int* tokens, float* top2,
                         float* scratch, cudaStream_t stream) {
+  ProfScope prof_(kProfOther, stream);
   RB_REQUIRE(H <= 32 * kMaxKPerLane, -6, "decode kernel supports hidden_features <= %d (got %d)", 32 * kMaxKPerLane, H);
   if (N <= 0) return 0;
   float* hbuf = scratch;

@@ -205,6 +205,7 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 
 int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, int grid,
                    cudaStream_t stream) {
+  ProfScope prof_(kProfDh, stream);
   const size_t smem = SmemLayout::total + 1024;
   RB_CUDA_CHECK(cudaFuncSetAttribute(dh_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dh_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmG, tmWmn, args);

@@ -174,6 +174,7 @@ __global__ void db_kernel(const __nv_bfloat16* __restrict__ g_ring, const int* _
 }  // namespace
 
 int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream) {
+  ProfScope prof_(kProfDw, stream);
   const size_t smem = SmemLayout::total + 1024;
   RB_CUDA_CHECK(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk_total = (args.Hp + kBN - 1) / kBN;
@@ -185,6 +186,7 @@ int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwA
 
 int launch_db(const __nv_bfloat16* g_ring, const int* tile_off, int B, int tile_begin, int tile_cap, int V, int Vp,
               float* db, cudaStream_t stream) {
+  ProfScope prof_(kProfDb, stream);
   dim3 grid((Vp / 2 + 31) / 32, 64);
   db_kernel<<<grid, 256, 0, stream>>>(g_ring, tile_off, B, tile_begin, tile_cap, V, Vp, db);
   RB_CUDA_CHECK(cudaGetLastError());

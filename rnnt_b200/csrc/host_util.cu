@@ -4,6 +4,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 namespace rb {
 
 static thread_local char g_err[512] = "";
@@ -63,6 +66,55 @@ int device_sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+namespace {
+struct ProfRec { int family; cudaEvent_t start, end; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+}  // namespace
+
+ProfScope::ProfScope(int family, cudaStream_t stream) : family_(family), stream_(stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  on_ = g_prof_on;
+  if (on_) {
+    cudaEventCreate(&start_);
+    cudaEventRecord(start_, stream_);
+  }
+}
+ProfScope::~ProfScope() {
+  if (!on_) return;
+  cudaEvent_t end;
+  cudaEventCreate(&end);
+  cudaEventRecord(end, stream_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back({family_, start_, end});
+}
+int prof_begin() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) { cudaEventDestroy(r.start); cudaEventDestroy(r.end); }
+  g_prof_recs.clear();
+  g_prof_on = true;
+  return 0;
+}
+int prof_end(float* ms, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  for (int i = 0; i < kProfFamilies; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  int rc = 0;
+  for (auto& r : g_prof_recs) {
+    cudaError_t e = cudaEventSynchronize(r.end);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.start, r.end);
+    if (e != cudaSuccess) { set_error("profile: %s", cudaGetErrorString(e)); rc = static_cast<int>(e); }
+    ms[r.family] += t;
+    launches[r.family] += 1;
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.end);
+  }
+  g_prof_recs.clear();
+  return rc;
 }
 
 }  // namespace rb

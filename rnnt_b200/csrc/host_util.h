@@ -34,4 +34,19 @@ int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t in
 
 int device_sm_count();
 
+// Opt-in per-kernel-family timing (CUDA events on the launch stream) and launch counting; used by bench.py to
+// compute the live roofline numbers.  Off by default: the hot path then records nothing.
+enum ProfFamily { kProfPrep = 0, kProfJointF = 1, kProfLattice = 2, kProfJointG = 3, kProfDh = 4, kProfDw = 5,
+                  kProfDb = 6, kProfOther = 7, kProfFamilies = 8 };
+struct ProfScope {
+  ProfScope(int family, cudaStream_t stream);
+  ~ProfScope();
+  int family_;
+  cudaStream_t stream_;
+  cudaEvent_t start_ = nullptr;
+  bool on_ = false;
+};
+int prof_begin();
+int prof_end(float* ms, long long* launches);
+
 }  // namespace rb

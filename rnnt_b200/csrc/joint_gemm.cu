@@ -369,6 +369,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
 int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
                       const JointArgs& args, int grid, cudaStream_t stream) {
+  ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
   const size_t smem = joint_gemm_smem_bytes();
   if (mode == 0) {
     RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

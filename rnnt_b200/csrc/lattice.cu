@@ -222,6 +222,7 @@ __global__ void dense_grads_kernel(const float* __restrict__ logits, const int* 
 
 int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
                       cudaStream_t stream) {
+  ProfScope prof_(kProfPrep, stream);
   tile_table_kernel<<<1, 32, 0, stream>>>(T_len, U_len, B, T, U1, tile_off, err_flag);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -229,6 +230,7 @@ int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, 
 
 int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __nv_bfloat16* Wb,
                            float* bias2, cudaStream_t stream) {
+  ProfScope prof_(kProfPrep, stream);
   const long long n = static_cast<long long>(Vp) * Hp;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 4096));
   convert_weights_kernel<<<grid, 256, 0, stream>>>(W, bias, V, H, Vp, Hp, Wb, bias2);
@@ -238,6 +240,7 @@ int launch_convert_weights(const float* W, const float* bias, int V, int H, int 
 
 int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, int T, int U1, float* alpha,
                    float* beta, float* costs, cudaStream_t stream) {
+  ProfScope prof_(kProfLattice, stream);
   const int threads = ((U1 + 31) / 32) * 32;
   RB_REQUIRE(threads <= 1024, -5, "lattice kernel supports U+1 <= 1024 (got %d)", U1);
   const size_t smem = 2 * (threads + 2) * sizeof(float);
@@ -248,6 +251,7 @@ int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, i
 
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
                 const int* T_len, const int* U_len, int B, int T, int U1, float4* coef, cudaStream_t stream) {
+  ProfScope prof_(kProfPrep, stream);
   const long long n = static_cast<long long>(B) * T * U1;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8));
   coef_kernel<<<grid, 256, 0, stream>>>(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef);
@@ -257,6 +261,7 @@ int launch_coef(const float* lp, const float* lse, const float* alpha, const flo
 
 int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
                           int B, int T, int U1, int V, int blank, float* lp, float* lse, cudaStream_t stream) {
+  ProfScope prof_(kProfOther, stream);
   const long long ncell = static_cast<long long>(B) * T * U1;
   const int grid = static_cast<int>(std::min<long long>((ncell + 7) / 8, 148 * 16));
   dense_logprobs_kernel<<<grid, 256, 0, stream>>>(logits, targets, tgt_ld, T_len, U_len, B, T, U1, V, blank, lp, lse);
@@ -267,6 +272,7 @@ int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, c
 int launch_dense_grads(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
                        const float4* coef, int B, int T, int U1, int V, int blank, float clamp, float* grads,
                        cudaStream_t stream) {
+  ProfScope prof_(kProfOther, stream);
   const long long ncell = static_cast<long long>(B) * T * U1;
   const int grid = static_cast<int>(std::min<long long>((ncell + 7) / 8, 148 * 16));
   dense_grads_kernel<<<grid, 256, 0, stream>>>(logits, targets, tgt_ld, T_len, U_len, coef, B, T, U1, V, blank,

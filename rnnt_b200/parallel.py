@@ -39,7 +39,7 @@ class GradAllReducer:
         self.average = average
         self.group = group
         self._flat = None
-        self._stream = torch.cuda.Stream() if torch.cuda.is_available() and self.params and self.params[0].is_cuda else None
+        self._stream = None   # created lazily on the first CUDA all-reduce
 
     def numel(self) -> int:
         return sum(p.numel() for p in self.params)
@@ -51,6 +51,8 @@ class GradAllReducer:
         n = sum(g.numel() for g in grads)
         if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device:
             self._flat = torch.empty(n, dtype=grads[0].dtype, device=grads[0].device)
+        if grads[0].is_cuda and self._stream is None:
+            self._stream = torch.cuda.Stream(device=grads[0].device)
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream())
             ctx = torch.cuda.stream(self._stream)

@@ -1,0 +1,278 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI / public API, against the oracle.
+
+Tolerances (stated once):
+  * per-utterance loss: relative 1e-4 vs the fp32 reference (north_star bar), bf16 tensor-core GEMM inside;
+  * gradients (bf16 operands, fp32 accumulation): relative Frobenius error <= 2e-2 vs the fp32 reference and
+    <= 6e-3 vs a reference whose GEMM operands are rounded to bf16 (the error of a bf16 torch baseline itself);
+  * lattice / dense-logits kernels (fp32 throughout): 1e-5 relative;  decode tokens: exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import fused_raw, make_inputs, rel_err, torch_reference
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_TOL_FP32 = 2e-2
+GRAD_TOL_BF16 = 6e-3
+
+
+def _golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    t = lambda k, dt=None: torch.from_numpy(g[k]).cuda() if dt is None else torch.from_numpy(g[k]).to(dt).cuda()
+    inp = dict(enc=t("enc"), pred=t("pred"), W=t("W"), b=t("b"), targets=t("targets", torch.int32),
+               T_len=t("T_len", torch.int32), U_len=t("U_len", torch.int32))
+    return g, inp
+
+
+@pytest.mark.parametrize("name", ["loss_tiny", "loss_mid", "loss_wide"])
+def test_fused_matches_reference_golden(golden_dir, name):
+    """Committed vectors produced by the reference itself (JointNetwork + torchaudio rnnt_loss, fp32 CPU)."""
+    g, inp = _golden(golden_dir, name)
+    out = fused_raw(inp)
+    assert out["status"] == 0
+    costs = out["costs"].cpu().numpy()
+    assert np.abs(costs - g["costs"]).max() <= LOSS_RTOL * np.abs(g["costs"]).max(), (costs, g["costs"])
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        r, _ = rel_err(out[k].cpu(), torch.from_numpy(g[k]))
+        assert r <= GRAD_TOL_FP32, (k, r)
+
+
+@pytest.mark.parametrize("shape", [(2, 20, 9, 64, 256, True), (3, 37, 13, 128, 512, True),
+                                   (2, 33, 17, 1024, 1024, False), (4, 200, 40, 1024, 1024, False)])
+def test_fused_vs_oracle_same_device(shape):
+    """Config (i) of BASELINE.json (B=4,T=200,U=40,H=V=1024) and smaller ragged cases vs the torchaudio path."""
+    B, T, U, H, V, ragged = shape
+    inp = make_inputs(B, T, U, H, V, ragged=ragged)
+    ref = torch_reference(inp)
+    refq = torch_reference(inp, emulate_bf16=True)
+    out = fused_raw(inp)
+    r, _ = rel_err(out["costs"], ref["costs"])
+    assert (out["costs"] - ref["costs"]).abs().max() <= LOSS_RTOL * ref["costs"].abs().max()
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert rel_err(out[k], ref[k])[0] <= GRAD_TOL_FP32, (k, rel_err(out[k], ref[k]))
+        assert rel_err(out[k], refq[k])[0] <= GRAD_TOL_BF16, (k, rel_err(out[k], refq[k]))
+
+
+def test_multi_chunk_backward_equals_single_chunk():
+    inp = make_inputs(2, 40, 20, 256, 1024, ragged=True)
+    one = fused_raw(inp)
+    many = fused_raw(inp, ring_tiles=7)
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert rel_err(many[k], one[k])[0] < 1e-5, k
+
+
+def test_padded_cells_have_zero_gradient_and_edge_lengths():
+    # U_b = 0 (pure blank path), T_b = 1, and a fully ragged batch; padded frames / labels get exactly zero grads
+    inp = make_inputs(4, 18, 6, 64, 256, ragged=True, seed=7)
+    inp["T_len"] = torch.tensor([18, 1, 9, 5], dtype=torch.int32, device="cuda")
+    inp["U_len"] = torch.tensor([6, 3, 0, 6], dtype=torch.int32, device="cuda")
+    ref = torch_reference(inp)
+    out = fused_raw(inp)
+    assert (out["costs"] - ref["costs"]).abs().max() <= LOSS_RTOL * ref["costs"].abs().max()
+    for b in range(4):
+        Tb, Ub = int(inp["T_len"][b]), int(inp["U_len"][b])
+        assert not out["d_enc"][b, Tb:].any()
+        assert not out["d_pred"][b, Ub + 1:].any()
+    # known answer: U_b = 0 -> cost = -sum_t lpB[t, 0]
+    b = 2
+    assert abs(float(out["costs"][b]) + float(out["lp"][b, :9, 0, 0].sum())) < 1e-3
+
+
+def test_linearity_in_dcost_and_mean_reduction():
+    import rnnt_b200
+    inp = make_inputs(3, 25, 7, 64, 256, ragged=True, seed=3)
+    one = fused_raw(inp)
+    dc = torch.tensor([0.5, -2.0, 3.0], device="cuda")
+    scaled = fused_raw(inp, dcost=dc)
+    # d_enc rows scale per utterance exactly like dcost (same kernels, same order -> tight tolerance)
+    for b in range(3):
+        assert rel_err(scaled["d_enc"][b], one["d_enc"][b] * dc[b])[0] < 2e-3
+    enc = inp["enc"].clone().requires_grad_(True)
+    loss = rnnt_b200.joint_rnnt_loss(enc, inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"],
+                                     inp["U_len"], reduction="mean")
+    assert abs(float(loss) - float(one["costs"].mean())) < 1e-4 * abs(float(loss))
+    loss.backward()
+    assert rel_err(enc.grad, one["d_enc"] / 3)[0] < 2e-3
+
+
+def test_clamp_matches_torchaudio():
+    import torchaudio
+    import rnnt_b200
+    inp = make_inputs(2, 12, 5, 64, 256, ragged=False, seed=5)
+    enc = inp["enc"].clone().requires_grad_(True)
+    loss = rnnt_b200.joint_rnnt_loss(enc, inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"],
+                                     inp["U_len"], clamp=0.01, reduction="sum")
+    loss.backward()
+    enc2 = inp["enc"].clone().requires_grad_(True)
+    logits = torch.nn.functional.linear(torch.tanh(enc2.unsqueeze(2) + inp["pred"].unsqueeze(1)), inp["W"], inp["b"])
+    ref = torchaudio.functional.rnnt_loss(logits, inp["targets"], inp["T_len"], inp["U_len"], clamp=0.01,
+                                          reduction="sum")
+    ref.backward()
+    assert rel_err(enc.grad, enc2.grad)[0] < GRAD_TOL_FP32
+
+
+def test_dense_loss_matches_torchaudio_and_golden(golden_dir):
+    import torchaudio
+    import rnnt_b200
+    g, inp = _golden(golden_dir, "loss_tiny")
+    logits = torch.from_numpy(g["logits"]).cuda().requires_grad_(True)
+    costs = rnnt_b200.rnnt_loss(logits, inp["targets"], inp["T_len"], inp["U_len"], reduction="none")
+    costs.sum().backward()
+    np.testing.assert_allclose(costs.detach().cpu().numpy(), g["costs"], rtol=1e-5)
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), g["dlogits"], atol=2e-6)
+    for (B, T, U, V) in [(4, 50, 20, 1024), (2, 400, 100, 64)]:
+        i2 = make_inputs(B, T, U, 16, V, ragged=True)
+        lg = torch.randn(B, T, U + 1, V, device="cuda").requires_grad_(True)
+        l2 = lg.detach().clone().requires_grad_(True)
+        mine = rnnt_b200.rnnt_loss(lg, i2["targets"], i2["T_len"], i2["U_len"], reduction="mean")
+        ref = torchaudio.functional.rnnt_loss(l2, i2["targets"], i2["T_len"], i2["U_len"], reduction="mean")
+        mine.backward(); ref.backward()
+        assert abs(float(mine) - float(ref)) < 1e-5 * abs(float(ref))
+        assert rel_err(lg.grad, l2.grad)[0] < 2e-4
+
+
+def test_lattice_kernel_vs_numpy_oracle():
+    import rnnt_b200
+    from oracle import rnnt_oracle as orc
+    rng = np.random.default_rng(0)
+    B, T, U1 = 3, 23, 9
+    lp = np.log(rng.uniform(0.05, 0.9, size=(B, T, U1, 2))).astype(np.float32)
+    T_len = np.array([23, 11, 1], np.int32); U_len = np.array([8, 0, 5], np.int32)
+    al, be, co = rnnt_b200.lattice(torch.from_numpy(lp).cuda(), torch.from_numpy(T_len).cuda(),
+                                   torch.from_numpy(U_len).cuda())
+    a_ref, b_ref, c_ref = orc.lattice(lp[..., 0].astype(np.float64), lp[..., 1].astype(np.float64), T_len, U_len)
+    np.testing.assert_allclose(co.cpu().numpy(), c_ref, rtol=1e-5)
+    for b in range(B):
+        sl = (b, slice(0, T_len[b]), slice(0, U_len[b] + 1))
+        np.testing.assert_allclose(al.cpu().numpy()[sl], a_ref[sl], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(be.cpu().numpy()[sl], b_ref[sl], rtol=1e-5, atol=1e-4)
+
+
+def test_error_behaviour_mirrors_torchaudio():
+    import rnnt_b200
+    inp = make_inputs(2, 10, 4, 64, 256)
+    with pytest.raises(RuntimeError, match="targets must be int32"):
+        rnnt_b200.joint_rnnt_loss(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"].long(), inp["T_len"],
+                                  inp["U_len"])
+    bad_T = inp["T_len"].clone(); bad_T[:] = 9
+    with pytest.raises(RuntimeError, match="input length mismatch"):
+        rnnt_b200.joint_rnnt_loss(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"], bad_T, inp["U_len"])
+    bad_U = inp["U_len"].clone(); bad_U[:] = 3
+    with pytest.raises(RuntimeError, match="output length mismatch"):
+        rnnt_b200.joint_rnnt_loss(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], bad_U)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rnnt_b200.joint_rnnt_loss(inp["enc"].cpu(), inp["pred"].cpu(), inp["W"].cpu(), inp["b"].cpu(),
+                                  inp["targets"].cpu(), inp["T_len"].cpu(), inp["U_len"].cpu())
+    logits = torch.randn(2, 10, 5, 7, device="cuda")
+    with pytest.raises(RuntimeError, match="logits must be contiguous"):
+        rnnt_b200.rnnt_loss(logits.transpose(1, 2).contiguous().transpose(1, 2), inp["targets"], inp["T_len"],
+                            inp["U_len"])
+
+
+def test_strided_encoder_view_is_accepted():
+    """audio_frame arrives as a (B,T,H) permuted view of (B,H,T) (rnnt/model.py:28)."""
+    import rnnt_b200
+    inp = make_inputs(2, 16, 5, 64, 256)
+    enc_bht = inp["enc"].permute(0, 2, 1).contiguous()
+    view = enc_bht.permute(0, 2, 1).requires_grad_(True)
+    assert not view.is_contiguous()
+    a = rnnt_b200.joint_rnnt_loss(view, inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"])
+    b = rnnt_b200.joint_rnnt_loss(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"],
+                                  inp["U_len"])
+    assert float(a) == float(b)
+    a.backward()
+    assert view.grad.shape == view.shape
+
+
+def test_joint_module_dropin_and_zero_edit_mode():
+    """JointNetwork keeps the reference's state_dict keys; the unmodified model.py:32-41 call pattern runs fused."""
+    import torchaudio
+    import rnnt_b200
+    torch.manual_seed(1)
+    joint = rnnt_b200.JointNetwork(-1, -1, 64, 256).cuda()
+    assert sorted(joint.state_dict().keys()) == ["joint_ln.bias", "joint_ln.weight"]
+    full = rnnt_b200.JointNetwork(32, 48, 64, 256).cuda()
+    assert "audio_ln.weight" in full.state_dict() and "text_ln.bias" in full.state_dict()
+    inp = make_inputs(2, 14, 6, 64, 256)
+    dense = joint(inp["enc"], inp["pred"])
+    assert dense.shape == (2, 14, 7, 256)
+    ref = torchaudio.functional.rnnt_loss(dense, inp["targets"], inp["T_len"], inp["U_len"], blank=-1, clamp=-1,
+                                          reduction="mean")
+    rnnt_b200.enable_zero_edit_mode(joint)
+    lazy = joint(inp["enc"], inp["pred"])                       # what rnnt/model.py:32 receives
+    assert isinstance(lazy, rnnt_b200.LazyJointLogits) and lazy.shape == dense.shape
+    loss = torchaudio.functional.rnnt_loss(logits=lazy, targets=inp["targets"], logit_lengths=inp["T_len"],
+                                           target_lengths=inp["U_len"], blank=-1, clamp=-1, reduction="mean")
+    assert abs(float(loss) - float(ref)) < LOSS_RTOL * abs(float(ref))
+    loss.backward()
+    assert joint.joint_ln.weight.grad is not None and joint.joint_ln.bias.grad is not None
+    # pre-projection variant (non-"convjs" configs, joint.py:8-12): grads reach audio_ln / text_ln
+    a = torch.randn(2, 14, 32, device="cuda"); t = torch.randn(2, 7, 48, device="cuda")
+    l2 = full.loss(a, t, inp["targets"], inp["T_len"], inp["U_len"])
+    l2.backward()
+    assert all(p.grad is not None for p in full.parameters())
+    with torch.no_grad():
+        d2 = full(a, t)
+    r2 = torchaudio.functional.rnnt_loss(d2, inp["targets"], inp["T_len"], inp["U_len"], reduction="mean")
+    assert abs(float(l2) - float(r2)) < LOSS_RTOL * abs(float(r2))
+
+
+def test_greedy_decode_matches_reference_golden(golden_dir):
+    """Token sequences produced by the reference's RNNTModel._greedy_decode_conv (fp32 CPU) -- must be exact."""
+    import rnnt_b200
+    g = np.load(os.path.join(golden_dir, "decode_small.npz"))
+    V, H = g["W"].shape
+    E = g["pred.embedding.weight"].shape[1]
+    joint = rnnt_b200.JointNetwork(-1, -1, H, V)
+    joint.load_state_dict({"joint_ln.weight": torch.from_numpy(g["W"]), "joint_ln.bias": torch.from_numpy(g["b"])})
+    pred = rnnt_b200.ConvPredictor(V, H, E, 0.3)
+    pred.load_state_dict({k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("pred.")})
+    model = rnnt_b200.RNNTModel(pred, torch.nn.Identity(), joint).cuda().eval()
+    feats = torch.from_numpy(g["feats"]).cuda()
+    got, margins = model.greedy_decode_features(feats, torch.from_numpy(g["T_len"]), max_length=int(g["max_length"]),
+                                                return_margins=True)
+    off = 0
+    for i, n in enumerate(g["tok_len"]):
+        want = g["tok_flat"][off:off + n].tolist()
+        off += n
+        assert got[i] == want, (i, min(margins[i]))
+
+
+def test_decode_step_full_width_vs_fp64():
+    import rnnt_b200
+    torch.manual_seed(0)
+    N, H, V = 64, 1024, 1024
+    a, p = torch.randn(N, H, device="cuda"), torch.randn(N, H, device="cuda")
+    W, b = torch.randn(V, H, device="cuda") / 32, torch.randn(V, device="cuda") * 0.1
+    tok, mg = rnnt_b200.joint_argmax(a, p, W, b, return_margin=True)
+    ref = torch.tanh(a.double() + p.double()) @ W.double().T + b.double()
+    bad = tok.long() != ref.argmax(-1)
+    # a flip is only tolerable at a numerical tie; report the margin if it ever happens
+    assert not bad.any(), mg[bad]
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (B=32,T=400,U=100,H=V=1024): size-independent checks, no dense reference."""
+    inp = make_inputs(32, 400, 100, 1024, 1024, ragged=False, seed=99)
+    out = fused_raw(inp)
+    costs = out["costs"]
+    assert torch.isfinite(costs).all() and (costs > 0).all()
+    # -beta[0,0] == -(alpha[T-1,U] + lpB[T-1,U])  (both directions of the lattice agree)
+    tail = -(out["alpha"][:, -1, -1] + out["lp"][:, -1, -1, 0])
+    assert (tail - costs).abs().max() <= 2e-5 * costs.abs().max()
+    # sum_v dlogits = 0 for every cell  =>  sum(db) == 0 up to bf16 rounding of ~1.3M gradient rows
+    assert abs(float(out["db"].sum())) < 1e-2 * float(out["db"].abs().sum())
+    # a second run is bit-identical in the forward and close in the (atomic-order dependent) backward
+    again = fused_raw(inp)
+    assert torch.equal(again["costs"], costs)
+    assert rel_err(again["dW"], out["dW"])[0] < 1e-5
+    # utterance 0 alone gives the same cost and the same d_enc row block
+    sub = {k: (v[:1].contiguous() if k in ("enc", "pred", "targets", "T_len", "U_len") else v) for k, v in inp.items()}
+    solo = fused_raw(sub)
+    assert torch.equal(solo["costs"][0], costs[0])
+    assert rel_err(solo["d_enc"][0], out["d_enc"][0])[0] < 1e-5
