@@ -35,7 +35,7 @@ const char* rnnt_b200_last_error(void);
 /* Upper bound on the number of 16(t) x 8(u) lattice tiles of a (B,T,U1) batch. */
 int64_t rnnt_b200_max_tiles(int B, int T, int U1);
 
-/* Workspace sizes in bytes.  ring_tiles = number of 128-cell tiles the backward's bf16 gradient / activation
+/* Workspace sizes in bytes.  ring_tiles = number of 128-cell tiles the backward's 16-bit gradient / activation
  * rings hold at once (fixed size, independent of B*T*U1); the backward walks the batch in chunks of that size. */
 int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, size_t* fwd_bytes,
                               size_t* bwd_bytes);
@@ -95,9 +95,9 @@ int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
 
 /* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
  *   offsets[0] tile table (B+1 int32 prefix sums of tiles per utterance, then one status int)
- *   offsets[1] W as bf16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
+ *   offsets[1] W as fp16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
  *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] bf16
- *   offsets[5] activation ring h [ring_tiles*128, Hp] bf16     offsets[6] total bytes.
+ *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16     offsets[6] total bytes.
  * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
 int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int64_t* offsets /*[8]*/,
                               int* Hp, int* Vp);

@@ -1,5 +1,6 @@
 // C-ABI entry points (see include/rnnt_b200.h).  Plain pointers and sizes only; every buffer is caller-owned.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -24,7 +25,7 @@ WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles) {
   w.Hp = round_up(H, 64);
   w.Vp = round_up(V, 256);
   size_t off = 0;
-  w.tile_off = off; off = align_up(off + (static_cast<size_t>(B) + 2) * sizeof(int), 1024);
+  w.tile_off = off; off = align_up(off + (static_cast<size_t>(B) + 4) * sizeof(int), 1024);   // + status, {S, 1/S}
   w.wb = off;       off = align_up(off + static_cast<size_t>(w.Vp) * w.Hp * 2, 1024);
   w.bias2 = off;    off = align_up(off + static_cast<size_t>(w.Vp) * 4, 1024);
   w.total_fwd = off;
@@ -100,10 +101,10 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   RB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7, "workspace must be 256-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* tile_off = reinterpret_cast<int*>(ws + w.tile_off);
-  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(ws + w.wb);
+  __half* Wb = reinterpret_cast<__half*>(ws + w.wb);
   float* bias2 = reinterpret_cast<float*>(ws + w.bias2);
 
-  rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, status, stream);
+  rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, status, nullptr, nullptr, stream);
   if (rc) return rc;
   rc = rb::launch_convert_weights(W, bias, V, H, w.Vp, w.Hp, Wb, bias2, stream);
   if (rc) return rc;
@@ -119,7 +120,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
   a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
   a.tile_begin = 0; a.tile_cap = 0x3fffffff;
-  a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.clamp = 0.f;
+  a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
   const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
   const int grid = static_cast<int>(std::min<int64_t>(rb::device_sm_count(), max_tiles));
   rc = rb::launch_joint_gemm(0, tmW, tmW, tmW, a, grid, stream);
@@ -144,11 +145,11 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   RB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7, "workspace must be 256-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* tile_off = reinterpret_cast<int*>(ws + w.tile_off);
-  __nv_bfloat16* Wb = reinterpret_cast<__nv_bfloat16*>(ws + w.wb);
+  __half* Wb = reinterpret_cast<__half*>(ws + w.wb);
   float* bias2 = reinterpret_cast<float*>(ws + w.bias2);
   float4* coef = reinterpret_cast<float4*>(ws + w.coef);
-  __nv_bfloat16* g_ring = reinterpret_cast<__nv_bfloat16*>(ws + w.g_ring);
-  __nv_bfloat16* h_ring = reinterpret_cast<__nv_bfloat16*>(ws + w.h_ring);
+  __half* g_ring = reinterpret_cast<__half*>(ws + w.g_ring);
+  __half* h_ring = reinterpret_cast<__half*>(ws + w.h_ring);
   const uint64_t ring_rows = static_cast<uint64_t>(ring_tiles) * kTileM;
 
   RB_CUDA_CHECK(cudaMemsetAsync(d_enc, 0, static_cast<size_t>(B) * T * H * 4, stream));
@@ -156,14 +157,15 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   RB_CUDA_CHECK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * 4, stream));
   RB_CUDA_CHECK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream));
 
-  rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, nullptr, stream);
+  float* gscale = reinterpret_cast<float*>(tile_off + B + 2);
+  rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, nullptr, dcost, gscale, stream);
   if (rc) return rc;
   rc = rb::launch_convert_weights(W, bias, V, H, w.Vp, w.Hp, Wb, bias2, stream);
   if (rc) return rc;
-  rc = rb::launch_coef(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef, stream);
+  rc = rb::launch_coef(lp, lse, alpha, beta, dcost, gscale, T_len, U_len, B, T, U1, coef, stream);
   if (rc) return rc;
 
-  CUtensorMap tmW, tmWmn, tmGst, tmHst, tmGmn, tmHmn;
+  CUtensorMap tmW, tmWmn, tmGst, tmG256, tmHst, tmGmn, tmHmn;
   // W [Vp, Hp]: K-major boxes (64 k x 256 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
   rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
   if (rc) return rc;
@@ -173,6 +175,8 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   rc = rb::make_tmap_2d(&tmGst, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmHst, h_ring, 2, w.Hp, ring_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmG256, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 256);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmGmn, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 64);
   if (rc) return rc;
@@ -194,27 +198,28 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
     a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
     a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles);
-    a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.clamp = clamp;
+    a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     rc = rb::launch_joint_gemm(1, tmW, tmGst, tmHst, a, grid, stream);
     if (rc) return rc;
 
     rb::DhArgs d{};
-    d.h_ring = h_ring; d.T_len = T_len; d.U_len = U_len; d.tile_off = tile_off;
+    d.enc = enc; d.enc_sb = enc_sb; d.enc_st = enc_st;
+    d.pred = pred; d.pred_sb = static_cast<long long>(U1) * H; d.pred_su = H; d.gscale = gscale;
+    d.T_len = T_len; d.U_len = U_len; d.tile_off = tile_off;
     d.B = B; d.T = T; d.U1 = U1; d.H = H; d.Hp = w.Hp; d.Vp = w.Vp;
     d.tile_begin = tile_begin; d.tile_cap = static_cast<int>(ring_tiles);
-    d.d_enc = d_enc; d.d_pred = d_pred; d.dbg_dh = nullptr;
-    rc = rb::launch_dh_gemm(tmGst, tmWmn, d, grid, stream);
+    d.d_enc = d_enc; d.d_pred = d_pred;
+    const int64_t dh_items = ((chunk_tiles + 1) / 2) * ((w.Hp + 127) / 128);
+    rc = rb::launch_dh_gemm(tmG256, tmWmn, d, static_cast<int>(std::min<int64_t>(sms, dh_items)), stream);
     if (rc) return rc;
 
     rb::DwArgs g{};
     g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
-    g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW;
+    g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW; g.db = dbias; g.gscale = gscale;
     const int out_tiles = (w.Vp / kTileM) * ((((w.Hp + 255) / 256) + 1) / 2);
     const int64_t kchunks = chunk_tiles * 2;
     g.ksplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms / std::max(1, out_tiles), kchunks)));
     rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, stream);
-    if (rc) return rc;
-    rc = rb::launch_db(g_ring, tile_off, B, tile_begin, static_cast<int>(ring_tiles), V, w.Vp, dbias, stream);
     if (rc) return rc;
   }
   return 0;
@@ -246,7 +251,7 @@ int rnnt_b200_loss_dense_bwd(const float* logits, const int32_t* targets, const 
   RB_REQUIRE(!(clamp > 0.f && dcost != nullptr), -9,
              "dense backward: clamp > 0 requires dcost == NULL (scale the returned gradients by dcost instead)");
   float4* coef = reinterpret_cast<float4*>(scratch_coef);
-  int rc = rb::launch_coef(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef, stream);
+  int rc = rb::launch_coef(lp, lse, alpha, beta, dcost, nullptr, T_len, U_len, B, T, U1, coef, stream);
   if (rc) return rc;
   return rb::launch_dense_grads(logits, targets, U1 - 1, T_len, U_len, coef, B, T, U1, V, blank, clamp, grads, stream);
 }

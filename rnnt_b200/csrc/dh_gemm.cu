@@ -1,31 +1,32 @@
-// Backward contraction #2:  dh = g . W  (K = V), fused with the tanh backward and the broadcast reductions.
+// Backward contraction #2, transposed:  dh^T[k, c] = sum_v W[v,k] * g[c,v]   (M = hidden unit k, N = lattice cell c),
+// fused with the tanh backward and the two broadcast reductions.
 //
 // Replaces autograd through rnnt/joint.py:32-39 for the activations:
-//   dz[c,k]       = (sum_v g[c,v] W[v,k]) * (1 - h[c,k]^2)
+//   dz[c,k]       = dh[c,k] * (1 - tanh(enc[b,t,k] + pred[b,u,k])^2)
 //   d_enc[b,t,k]  = sum_u dz[b,t,u,k]      d_pred[b,u,k] = sum_t dz[b,t,u,k]
-// A operand: gradient ring g [ring_rows, Vp] bf16 (K-major, TMA).  B operand: W^T read as an MN-major
-// view of the same bf16 W[Vp, Hp] buffer the forward uses (no transposed copy).
-// Tile = 128 lattice cells (16 t x 8 u) x 512 hidden columns (two 256-column TMEM accumulators).
-// Epilogue: TMEM -> dz -> padded smem transpose -> per-(t,k) / per-(u,k) partial sums -> coalesced fp32 atomics.
+// Putting the hidden unit on the TMEM lane makes a thread own ONE k and 32 consecutive cells (= 4 t x 8 u of a
+// lattice tile) per tcgen05.ld: both reductions are plain register sums, tanh' is recomputed from 4 enc + 8 pred
+// values per thread (MUFU is otherwise idle here), and the fp32 atomics are coalesced over k.
+//   A operand: W^T block (128 k x 64 v) = MN-major view of the fp16 W[Vp,Hp] buffer (TMA, two 64x64 boxes)
+//   B operand: gradient ring g [ring_rows, Vp] fp16, K-major (TMA, one 64 x 256 box = two lattice tiles)
+// Work item = (pair of lattice tiles, block of 128 hidden units); accumulators ping-pong between the two halves of
+// TMEM so the epilogue of item i overlaps the MMAs of item i+1.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace rb {
 namespace {
 
-constexpr int kStagesA = 3;
-constexpr int kStagesB = 4;
-constexpr int kBytesA = kTileM * kBK * 2;   // 16 KB (128 cells x 64 v)
-constexpr int kBytesB = kBK * kBN * 2;      // 32 KB (64 v x 256 k), four 64x64 MN-major boxes
+constexpr int kStages = 4;
+constexpr int kBytesA = kBK * 128 * 2;      // 16 KB: 64 v x 128 k
+constexpr int kBytesB = kBN * kBK * 2;      // 32 KB: 256 cells x 64 v
 constexpr int kNumThreads = 192;
 constexpr int kTmemCols = 512;
-constexpr int kTbStride = 33;
 
 struct SmemLayout {
   static constexpr int b_ring = 0;
-  static constexpr int a_ring = b_ring + kStagesB * kBytesB;
-  static constexpr int tbuf = a_ring + kStagesA * kBytesA;
-  static constexpr int bars = tbuf + 2 * kTileM * kTbStride * 4;
+  static constexpr int a_ring = b_ring + kStages * kBytesB;
+  static constexpr int bars = a_ring + kStages * kBytesA;
   static constexpr int total = bars + 256;
 };
 
@@ -36,27 +37,25 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_ring = smem_base + SmemLayout::b_ring;
   const uint32_t a_ring = smem_base + SmemLayout::a_ring;
-  float* tbuf = reinterpret_cast<float*>(smem_gen + SmemLayout::tbuf);
   const uint32_t bars = smem_base + SmemLayout::bars;
-  const uint32_t b_full = bars, b_empty = bars + 8 * kStagesB;
-  const uint32_t a_full = bars + 16 * kStagesB, a_empty = a_full + 8 * kStagesA;
-  const uint32_t tmem_full = a_empty + 8 * kStagesA, tmem_empty = tmem_full + 8;
+  const uint32_t full = bars, empty = bars + 8 * kStages;
+  const uint32_t tmem_full = bars + 16 * kStages, tmem_empty = tmem_full + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = __ldg(p.tile_off + p.B);
   const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
+  const int ntiles = max(0, tile_end - p.tile_begin);
+  const int ncb = (ntiles + 1) / 2;                 // cell blocks of 2 lattice tiles (256 ring rows)
+  const int nhb = (p.Hp + 127) / 128;               // hidden blocks of 128
+  const int nitems = ncb * nhb;
   const int nk = p.Vp / kBK;
-  const int nblk_total = (p.Hp + kBN - 1) / kBN;
-  const int npass = (nblk_total + 1) / 2;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmG);
     tma_prefetch_desc(&tmWmn);
-    for (int s = 0; s < kStagesB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    for (int s = 0; s < kStagesA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
@@ -67,132 +66,104 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t ita = 0, itb = 0;
-      for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        const int ring_row0 = (tile - p.tile_begin) * kTileM;
-        for (int pass = 0; pass < npass; ++pass) {
-          const int nblk = min(2, nblk_total - pass * 2);
-          for (int kc = 0; kc < nk; ++kc, ++ita) {
-            const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
-            mbar_wait(a_empty + 8 * sa, pha ^ 1);
-            mbar_expect_tx(a_full + 8 * sa, kBytesA);
-            tma_load_2d(a_ring + sa * kBytesA, &tmG, a_full + 8 * sa, kc * kBK, ring_row0);
-            for (int blk = 0; blk < nblk; ++blk, ++itb) {
-              const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
-              mbar_wait(b_empty + 8 * sb, phb ^ 1);
-              mbar_expect_tx(b_full + 8 * sb, kBytesB);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                tma_load_2d(b_ring + sb * kBytesB + j * 8192, &tmWmn, b_full + 8 * sb,
-                            (pass * 2 + blk) * kBN + j * 64, kc * kBK);
-            }
-          }
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int cb = item / nhb, hb = item % nhb;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(full + 8 * s, kBytesA + kBytesB);
+          tma_load_2d(a_ring + s * kBytesA, &tmWmn, full + 8 * s, hb * 128, kc * kBK);
+          tma_load_2d(a_ring + s * kBytesA + 8192, &tmWmn, full + 8 * s, hb * 128 + 64, kc * kBK);
+          tma_load_2d(b_ring + s * kBytesB, &tmG, full + 8 * s, kc * kBK, cb * 256);
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(kTileM, kBN, 0, 1);
-    uint32_t ita = 0, itb = 0, pc = 0;
-    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-      for (int pass = 0; pass < npass; ++pass, ++pc) {
-        const int nblk = min(2, nblk_total - pass * 2);
-        mbar_wait(tmem_empty, (pc & 1) ^ 1);
+    constexpr uint32_t idesc = make_idesc(128, kBN, 1, 0, kFmtF16, kFmtF16);
+    uint32_t it = 0, ic = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
+      const uint32_t acc = ic & 1, accph = (ic >> 1) & 1;
+      mbar_wait(tmem_empty + 8 * acc, accph ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < nk; ++kc, ++it) {
+        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+        mbar_wait(full + 8 * s, ph);
         tc_fence_after();
-        for (int kc = 0; kc < nk; ++kc, ++ita) {
-          const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
-          mbar_wait(a_full + 8 * sa, pha);
-          for (int blk = 0; blk < nblk; ++blk, ++itb) {
-            const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
-            mbar_wait(b_full + 8 * sb, phb);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = a_ring + sa * kBytesA, b_addr = b_ring + sb * kBytesB;
+        if (lane == 0) {
+          const uint32_t a_addr = a_ring + s * kBytesA, b_addr = b_ring + s * kBytesB;
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);        // K-major
-                const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);    // MN-major
-                umma_f16(tmem_base + blk * kBN, ad, bd, idesc, (kc | k) != 0);
-              }
-              umma_commit(b_empty + 8 * sb);
-            }
-            __syncwarp();
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);   // MN-major (W^T)
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);       // K-major (g)
+            umma_f16(tmem_base + acc * kBN, ad, bd, idesc, (kc | k) != 0);
           }
-          if (lane == 0) umma_commit(a_empty + 8 * sa);
-          __syncwarp();
+          umma_commit(empty + 8 * s);
         }
-        if (lane == 0) umma_commit(tmem_full);
         __syncwarp();
       }
+      if (lane == 0) umma_commit(tmem_full + 8 * acc);
+      __syncwarp();
     }
   } else {
     const int lane_grp = warp & 3;
-    const int row = lane_grp * 32 + lane;
-    const int epi_tid = (warp - 2) * 32 + lane;
-    const int rcol = epi_tid & 31, part = epi_tid >> 5;
-    uint32_t pc = 0, cc = 0;
-    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
-      const int ring_row = (tile - p.tile_begin) * kTileM + row;
-      const __nv_bfloat16* hrow = p.h_ring + static_cast<long long>(ring_row) * p.Hp;
-      for (int pass = 0; pass < npass; ++pass, ++pc) {
-        const int nblk = min(2, nblk_total - pass * 2);
-        mbar_wait(tmem_full, pc & 1);
-        tc_fence_after();
-        for (int c32 = 0; c32 < nblk * (kBN / 32); ++c32) {
-          const int col0 = pass * 2 * kBN + c32 * 32;
-          if (col0 >= p.Hp) break;   // uniform: remaining columns are zero padding
+    const int krow = lane_grp * 32 + lane;      // hidden unit within the block = TMEM lane
+    const float inv_s = __ldg(p.gscale + 1);
+    uint32_t ic = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
+      const int cb = item / nhb, hb = item % nhb;
+      const int k = hb * 128 + krow;
+      const bool k_ok = k < p.H;
+      const int kk = k_ok ? k : 0;
+      const uint32_t acc = ic & 1, accph = (ic >> 1) & 1;
+      mbar_wait(tmem_full + 8 * acc, accph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int tile = p.tile_begin + cb * 2 + half;
+        if (tile >= tile_end) break;            // uniform
+        const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
+        float pv[8], su[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pv[j] = __ldg(p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + j, p.U1 - 1)) * p.pred_su + kk);
+          su[j] = 0.f;
+        }
+        const float* e_base = p.enc + tc.b * p.enc_sb + kk;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
           float v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + c32 * 32, v);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * kBN + half * 128 + q * 32, v);
+          float ev[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            ev[i] = __ldg(e_base + static_cast<long long>(min(tc.t0 + q * 4 + i, p.T - 1)) * p.enc_st);
           tmem_ld_wait();
-          if (p.dbg_dh != nullptr) {
-            float* d = p.dbg_dh + static_cast<long long>(ring_row) * p.Hp + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) d[j] = v[j];
-          }
-          const uint4* h4 = reinterpret_cast<const uint4*>(hrow + col0);
-          float* tb = tbuf + (cc & 1) * (kTileM * kTbStride);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 hh = __ldg(h4 + q);
-            const uint32_t w[4] = {hh.x, hh.y, hh.z, hh.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float h0 = bf16lo_to_f32(w[e]), h1 = bf16hi_to_f32(w[e]);
-              const int j = q * 8 + e * 2;
-              tb[row * kTbStride + j] = v[j] * (1.f - h0 * h0);
-              tb[row * kTbStride + j + 1] = v[j + 1] * (1.f - h1 * h1);
-            }
-          }
-          named_bar_sync(1, 128);
-          ++cc;
-          const int col = col0 + rcol;
-          if (col < p.H) {
-            float su[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) su[j] = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float st = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float x = tb[(part * 32 + i * 8 + j) * kTbStride + rcol];
-                st += x;
-                su[j] += x;
-              }
-              const int t = tc.t0 + part * 4 + i;
-              if (t < tc.Tb) atomicAdd(p.d_enc + (static_cast<long long>(tc.b) * p.T + t) * p.H + col, st);
-            }
+          for (int i = 0; i < 4; ++i) {
+            float st = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int u = tc.u0 + j;
-              if (u <= tc.Ub) atomicAdd(p.d_pred + (static_cast<long long>(tc.b) * p.U1 + u) * p.H + col, su[j]);
+              const float h = tanh_approx(ev[i] + pv[j]);
+              const float dz = v[i * 8 + j] * fmaf(-h, h, 1.f);
+              st += dz;
+              su[j] += dz;
             }
+            const int t = tc.t0 + q * 4 + i;
+            if (k_ok && t < tc.Tb)
+              atomicAdd(p.d_enc + (static_cast<long long>(tc.b) * p.T + t) * p.H + k, st * inv_s);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int u = tc.u0 + j;
+          if (k_ok && u <= tc.Ub)
+            atomicAdd(p.d_pred + (static_cast<long long>(tc.b) * p.U1 + u) * p.H + k, su[j] * inv_s);
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
     }
   }
 

@@ -4,7 +4,8 @@
 // Both operands are read as MN-major views of the row-major rings written by the G-mode joint kernel:
 //   A[m=v][k=c] = g_ring[c][v]      B[n=kh][k=c] = h_ring[c][kh]
 // One CTA owns a 128(v) x 512(k_h) block of dW (two TMEM accumulators = all 512 columns) for one K split and
-// adds it into the fp32 dW with vector reductions (red.global.add.v4.f32).
+// adds it into the fp32 dW with vector reductions (red.global.add.v4.f32).  The CTAs of the first k_h block also
+// produce db: while the MMAs run, their (otherwise idle) epilogue warps sum every A stage over its 64 cells.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -54,12 +55,13 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
   const int k_begin = static_cast<int>(static_cast<long long>(nkc) * ks / p.ksplit);
   const int k_end = static_cast<int>(static_cast<long long>(nkc) * (ks + 1) / p.ksplit);
   if (k_begin >= k_end) return;   // uniform over the CTA
+  const bool do_db = (ht == 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmGmn);
     tma_prefetch_desc(&tmHmn);
     for (int s = 0; s < kStagesB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    for (int s = 0; s < kStagesA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < kStagesA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, do_db ? 5 : 1); }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
   }
@@ -91,7 +93,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(kTileM, kBN, 1, 1);
+    constexpr uint32_t idesc = make_idesc(kTileM, kBN, 1, 1, kFmtF16, kFmtF16);
     uint32_t ita = 0, itb = 0;
     for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
       const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
@@ -121,6 +123,30 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + lane;
     const int v = vt * kTileM + row;
+    const float inv_s = __ldg(p.gscale + 1);
+    if (do_db) {
+      // column sums of g over the cells of every A stage (MN-major: 64 cell rows of 128 bytes per 64-v box)
+      const uint32_t col_off = (row >> 6) * 8192 + (row & 7) * 2;
+      const uint32_t chunk = (row & 63) >> 3;
+      float dsum = 0.f;
+      uint32_t ita = 0;
+      for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
+        const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
+        mbar_wait(a_full + 8 * sa, pha);
+        const uint32_t base = a_ring + sa * kBytesA + col_off;
+        float part = 0.f;
+#pragma unroll 16
+        for (int c = 0; c < kBK; ++c) {
+          uint16_t hbits;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hbits) : "r"(base + c * 128 + ((chunk ^ (c & 7)) << 4)));
+          part += __half2float(__ushort_as_half(hbits));
+        }
+        dsum += part;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty + 8 * sa);
+      }
+      if (v < p.V) atomicAdd(p.db + v, dsum * inv_s);
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     for (int c32 = 0; c32 < nblk * (kBN / 32); ++c32) {
@@ -134,13 +160,14 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (col0 + 4 * q + 3 < p.H) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(acc[4 * q]),
-                         "f"(acc[4 * q + 1]), "f"(acc[4 * q + 2]), "f"(acc[4 * q + 3])
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q),
+                         "f"(acc[4 * q] * inv_s), "f"(acc[4 * q + 1] * inv_s), "f"(acc[4 * q + 2] * inv_s),
+                         "f"(acc[4 * q + 3] * inv_s)
                          : "memory");
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (col0 + 4 * q + e < p.H) atomicAdd(dst + 4 * q + e, acc[4 * q + e]);
+              if (col0 + 4 * q + e < p.H) atomicAdd(dst + 4 * q + e, acc[4 * q + e] * inv_s);
           }
         }
       }
@@ -152,25 +179,6 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// db[v] = sum over ring rows of g[row, v]
-__global__ void db_kernel(const __nv_bfloat16* __restrict__ g_ring, const int* __restrict__ tile_off, int B,
-                          int tile_begin, int tile_cap, int V, int Vp, float* __restrict__ db) {
-  const int total_tiles = __ldg(tile_off + B);
-  const int tile_end = min(total_tiles, tile_begin + tile_cap);
-  const int nrows = max(0, tile_end - tile_begin) * kTileM;
-  const int col = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
-  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (col >= Vp) return;
-  float s0 = 0.f, s1 = 0.f;
-  for (int r = blockIdx.y * nw + wid; r < nrows; r += gridDim.y * nw) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(g_ring + static_cast<long long>(r) * Vp + col));
-    s0 += bf16lo_to_f32(w);
-    s1 += bf16hi_to_f32(w);
-  }
-  if (col < V) atomicAdd(db + col, s0);
-  if (col + 1 < V) atomicAdd(db + col + 1, s1);
-}
-
 }  // namespace
 
 int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream) {
@@ -180,15 +188,6 @@ int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwA
   const int nblk_total = (args.Hp + kBN - 1) / kBN;
   const int grid = (args.Vp / kTileM) * ((nblk_total + 1) / 2) * args.ksplit;
   dw_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmGmn, tmHmn, args);
-  RB_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-int launch_db(const __nv_bfloat16* g_ring, const int* tile_off, int B, int tile_begin, int tile_cap, int V, int Vp,
-              float* db, cudaStream_t stream) {
-  ProfScope prof_(kProfDb, stream);
-  dim3 grid((Vp / 2 + 31) / 32, 64);
-  db_kernel<<<grid, 256, 0, stream>>>(g_ring, tile_off, B, tile_begin, tile_cap, V, Vp, db);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

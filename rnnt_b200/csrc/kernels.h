@@ -1,6 +1,8 @@
 // Internal launch interface between the C-ABI layer (api.cu) and the kernels.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -24,13 +26,18 @@ struct JointArgs {
   int tile_begin, tile_cap;   // process tiles [tile_begin, min(total, tile_begin + tile_cap))
   float* lp;              // F: (B,T,U1,2) log-probs (blank, label)
   float* lse;             // F: (B,T,U1) log-sum-exp of the logits (natural log)
-  const float4* coef;     // G: (B,T,U1) (gamma*dc, eB*dc, eE*dc, lse)
+  const float4* coef;     // G: (B,T,U1) (gamma*dc*S, eB*dc*S, eE*dc*S, lse)
   const float* dcost;     // G: (B) or nullptr (only used to scale the clamp bound)
+  const float* gscale;    // G: {S, 1/S} power-of-two gradient scale
   float clamp;            // G: <= 0 disables (torchaudio's clamp argument, rnnt/model.py:40 passes -1)
 };
 
 struct DhArgs {
-  const __nv_bfloat16* h_ring;   // [ring_rows, Hp] tanh activations of the chunk (G mode output)
+  const float* enc;       // (B,T,H) fp32, H contiguous (tanh' is recomputed from the inputs)
+  long long enc_sb, enc_st;
+  const float* pred;      // (B,U1,H)
+  long long pred_sb, pred_su;
+  const float* gscale;    // {S, 1/S}
   const int* T_len;
   const int* U_len;
   const int* tile_off;
@@ -38,7 +45,6 @@ struct DhArgs {
   int tile_begin, tile_cap;
   float* d_enc;          // (B,T,H) fp32, accumulated with atomics (caller zero-fills)
   float* d_pred;         // (B,U1,H)
-  float* dbg_dh;         // optional [ring_rows, Hp] fp32 raw dh dump (tests), or nullptr
 };
 
 struct DwArgs {
@@ -46,6 +52,8 @@ struct DwArgs {
   int B, H, Hp, V, Vp;
   int tile_begin, tile_cap;
   float* dW;             // (V,H) fp32, accumulated with atomics (caller zero-fills)
+  float* db;             // (V) fp32, accumulated with atomics (column sums of g, taken from the A stages)
+  const float* gscale;   // {S, 1/S}
   int ksplit;
 };
 
@@ -58,15 +66,14 @@ int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwA
 
 // prep / small kernels (prep.cu, lattice.cu, decode.cu)
 int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
-                      cudaStream_t stream);
-int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __nv_bfloat16* Wb,
+                      const float* dcost, float* gscale, cudaStream_t stream);
+int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __half* Wh,
                            float* bias2, cudaStream_t stream);
 int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, int T, int U1, float* alpha,
                    float* beta, float* costs, cudaStream_t stream);
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
-                const int* T_len, const int* U_len, int B, int T, int U1, float4* coef, cudaStream_t stream);
-int launch_db(const __nv_bfloat16* g_ring, const int* tile_off, int B, int tile_begin, int tile_cap, int V, int Vp,
-              float* db, cudaStream_t stream);
+                const float* gscale, const int* T_len, const int* U_len, int B, int T, int U1, float4* coef,
+                cudaStream_t stream);
 int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
                           int B, int T, int U1, int V, int blank, float* lp, float* lse, cudaStream_t stream);
 int launch_dense_grads(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,

@@ -15,11 +15,30 @@
 namespace rb {
 namespace {
 
+// Also derives the exact power-of-two scale S that maps max_b |dcost_b| into (0.5, 1]: the backward stores
+// logit-gradients in fp16 as g*S (full use of fp16's range whatever the loss scaling) and its epilogues apply 1/S.
 __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __restrict__ U_len, int B, int T, int U1,
-                                  int* __restrict__ tile_off, int* __restrict__ err_flag) {
+                                  int* __restrict__ tile_off, int* __restrict__ err_flag,
+                                  const float* __restrict__ dcost, float* __restrict__ gscale) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int acc = 0, bad = 0;
   tile_off[0] = 0;
+  if (gscale) {
+    float mx = 0.f;
+    if (dcost) {
+      for (int b = 0; b < B; ++b) mx = fmaxf(mx, fabsf(dcost[b]));
+    } else {
+      mx = 1.f;
+    }
+    float S = 1.f;
+    if (mx > 0.f && mx < INFINITY) {
+      int e;
+      frexpf(mx, &e);          // mx = m * 2^e, m in [0.5, 1)
+      S = ldexpf(1.f, -e);     // mx * S in [0.5, 1)
+    }
+    gscale[0] = S;
+    gscale[1] = 1.f / S;
+  }
   for (int b = 0; b < B; ++b) {
     int Tb = T_len[b], Ub = U_len[b];
     if (Tb < 1 || Tb > T || Ub < 0 || Ub > U1 - 1) bad = 1;
@@ -32,13 +51,13 @@ __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __re
 }
 
 __global__ void convert_weights_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int H,
-                                       int Vp, int Hp, __nv_bfloat16* __restrict__ Wb, float* __restrict__ bias2) {
+                                       int Vp, int Hp, __half* __restrict__ Wh, float* __restrict__ bias2) {
   const long long n = static_cast<long long>(Vp) * Hp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int v = static_cast<int>(i / Hp), k = static_cast<int>(i % Hp);
     const float x = (v < V && k < H) ? W[static_cast<long long>(v) * H + k] : 0.f;
-    Wb[i] = __float2bfloat16_rn(x);
+    Wh[i] = __float2half_rn(x);
     if (k == 0) bias2[v] = (v < V) ? bias[v] * kLog2e : -1e30f;
   }
 }
@@ -127,8 +146,9 @@ __global__ void lattice_kernel(const float* __restrict__ lp, const int* __restri
 
 __global__ void coef_kernel(const float* __restrict__ lp, const float* __restrict__ lse,
                             const float* __restrict__ alpha, const float* __restrict__ beta,
-                            const float* __restrict__ dcost, const int* __restrict__ T_len,
-                            const int* __restrict__ U_len, int B, int T, int U1, float4* __restrict__ coef) {
+                            const float* __restrict__ dcost, const float* __restrict__ gscale,
+                            const int* __restrict__ T_len, const int* __restrict__ U_len, int B, int T, int U1,
+                            float4* __restrict__ coef) {
   const long long n = static_cast<long long>(B) * T * U1;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -138,7 +158,7 @@ __global__ void coef_kernel(const float* __restrict__ lp, const float* __restric
     const int Tb = max(1, min(T_len[b], T)), Ub = max(0, min(U_len[b], U1 - 1));
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < Tb && u <= Ub) {
-      const float dc = dcost ? dcost[b] : 1.f;
+      const float dc = (dcost ? dcost[b] : 1.f) * (gscale ? gscale[0] : 1.f);
       const float logZ = beta[static_cast<long long>(b) * T * U1];
       const float c = alpha[i] - logZ;
       const float2 l = reinterpret_cast<const float2*>(lp)[i];
@@ -221,19 +241,19 @@ __global__ void dense_grads_kernel(const float* __restrict__ logits, const int* 
 }  // namespace
 
 int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
-                      cudaStream_t stream) {
+                      const float* dcost, float* gscale, cudaStream_t stream) {
   ProfScope prof_(kProfPrep, stream);
-  tile_table_kernel<<<1, 32, 0, stream>>>(T_len, U_len, B, T, U1, tile_off, err_flag);
+  tile_table_kernel<<<1, 32, 0, stream>>>(T_len, U_len, B, T, U1, tile_off, err_flag, dcost, gscale);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __nv_bfloat16* Wb,
+int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __half* Wh,
                            float* bias2, cudaStream_t stream) {
   ProfScope prof_(kProfPrep, stream);
   const long long n = static_cast<long long>(Vp) * Hp;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 4096));
-  convert_weights_kernel<<<grid, 256, 0, stream>>>(W, bias, V, H, Vp, Hp, Wb, bias2);
+  convert_weights_kernel<<<grid, 256, 0, stream>>>(W, bias, V, H, Vp, Hp, Wh, bias2);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -250,11 +270,12 @@ int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, i
 }
 
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
-                const int* T_len, const int* U_len, int B, int T, int U1, float4* coef, cudaStream_t stream) {
+                const float* gscale, const int* T_len, const int* U_len, int B, int T, int U1, float4* coef,
+                cudaStream_t stream) {
   ProfScope prof_(kProfPrep, stream);
   const long long n = static_cast<long long>(B) * T * U1;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8));
-  coef_kernel<<<grid, 256, 0, stream>>>(lp, lse, alpha, beta, dcost, T_len, U_len, B, T, U1, coef);
+  coef_kernel<<<grid, 256, 0, stream>>>(lp, lse, alpha, beta, dcost, gscale, T_len, U_len, B, T, U1, coef);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

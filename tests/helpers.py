@@ -72,9 +72,11 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0):
 def ring_views(out):
     ws, offs, Hp, Vp = out["ws"], out["offs"], out["Hp"], out["Vp"]
     rows = out["ring_tiles"] * 128
-    g = ws[offs[4]:offs[4] + rows * Vp * 2].view(torch.bfloat16).view(rows, Vp)
-    h = ws[offs[5]:offs[5] + rows * Hp * 2].view(torch.bfloat16).view(rows, Hp)
-    return g, h
+    g = ws[offs[4]:offs[4] + rows * Vp * 2].view(torch.float16).view(rows, Vp)
+    h = ws[offs[5]:offs[5] + rows * Hp * 2].view(torch.float16).view(rows, Hp)
+    B = out["costs"].numel()
+    scale = ws[offs[0] + (B + 2) * 4: offs[0] + (B + 4) * 4].view(torch.float32)   # {S, 1/S}
+    return g, h, float(scale[0])
 
 
 def tile_rows(T_len, U_len):
@@ -90,18 +92,21 @@ def tile_rows(T_len, U_len):
     return rows
 
 
-def torch_reference(inp, emulate_bf16=False, dcost=None):
-    """fp32 torch restatement on the SAME device (oracle/ref_path.py semantics), optionally with bf16-rounded
-    GEMM operands to separate kernel bugs from precision."""
+def torch_reference(inp, emulate_bf16=False, dcost=None, device=None):
+    """fp32 torch restatement on the SAME device (oracle/ref_path.py semantics), optionally with the joint GEMM
+    operands (tanh output, W) rounded to fp16 as the kernels do, to separate kernel bugs from precision."""
     import torchaudio
+    if device is not None:
+        inp = {k: v.to(device) for k, v in inp.items()}
+        dcost = None if dcost is None else dcost.to(device)
     enc = inp["enc"].detach().clone().requires_grad_(True)
     pred = inp["pred"].detach().clone().requires_grad_(True)
     W = inp["W"].detach().clone().requires_grad_(True)
     b = inp["b"].detach().clone().requires_grad_(True)
     h = torch.tanh(enc.unsqueeze(2) + pred.unsqueeze(1))
     if emulate_bf16:
-        h = h + (h.detach().bfloat16().float() - h.detach())
-        Wq = W + (W.detach().bfloat16().float() - W.detach())
+        h = h + (h.detach().half().float() - h.detach())
+        Wq = W + (W.detach().half().float() - W.detach())
     else:
         Wq = W
     logits = torch.nn.functional.linear(h, Wq, b)

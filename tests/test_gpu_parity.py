@@ -2,8 +2,8 @@
 
 Tolerances (stated once):
   * per-utterance loss: relative 1e-4 vs the fp32 reference (north_star bar), bf16 tensor-core GEMM inside;
-  * gradients (bf16 operands, fp32 accumulation): relative Frobenius error <= 2e-2 vs the fp32 reference and
-    <= 6e-3 vs a reference whose GEMM operands are rounded to bf16 (the error of a bf16 torch baseline itself);
+  * gradients (fp16 activations/weights, bf16 logit-gradients, fp32 accumulation): relative Frobenius error
+    <= 2e-2 vs the fp32 reference and <= 6e-3 vs a reference whose joint GEMM operands are rounded to fp16;
   * lattice / dense-logits kernels (fp32 throughout): 1e-5 relative;  decode tokens: exact.
 """
 import os
@@ -71,9 +71,11 @@ def test_padded_cells_have_zero_gradient_and_edge_lengths():
     inp = make_inputs(4, 18, 6, 64, 256, ragged=True, seed=7)
     inp["T_len"] = torch.tensor([18, 1, 9, 5], dtype=torch.int32, device="cuda")
     inp["U_len"] = torch.tensor([6, 3, 0, 6], dtype=torch.int32, device="cuda")
-    ref = torch_reference(inp)
+    ref = torch_reference(inp, device="cpu")   # torchaudio's CUDA kernels mishandle T_b=1 / U_b=0 rows; its CPU path is the oracle
     out = fused_raw(inp)
-    assert (out["costs"] - ref["costs"]).abs().max() <= LOSS_RTOL * ref["costs"].abs().max()
+    assert ((out["costs"].cpu() - ref["costs"]).abs() <= LOSS_RTOL * ref["costs"].abs()).all(), (out["costs"], ref["costs"])
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert rel_err(out[k].cpu(), ref[k])[0] <= GRAD_TOL_FP32, k
     for b in range(4):
         Tb, Ub = int(inp["T_len"][b]), int(inp["U_len"][b])
         assert not out["d_enc"][b, Tb:].any()
@@ -95,7 +97,7 @@ def test_linearity_in_dcost_and_mean_reduction():
     enc = inp["enc"].clone().requires_grad_(True)
     loss = rnnt_b200.joint_rnnt_loss(enc, inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"],
                                      inp["U_len"], reduction="mean")
-    assert abs(float(loss) - float(one["costs"].mean())) < 1e-4 * abs(float(loss))
+    assert abs(float(loss.detach()) - float(one["costs"].mean())) < 1e-4 * abs(float(loss.detach()))
     loss.backward()
     assert rel_err(enc.grad, one["d_enc"] / 3)[0] < 2e-3
 
