@@ -37,7 +37,8 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
+    extra = os.environ.get("RNNT_B200_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH + ".tmp"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

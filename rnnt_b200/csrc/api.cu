@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/rnnt_b200.h"
 #include "common.cuh"
@@ -120,6 +121,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
   a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
   a.tile_begin = 0; a.tile_cap = 0x3fffffff;
+  { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
   const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
   const int grid = static_cast<int>(std::min<int64_t>(rb::device_sm_count(), max_tiles));
@@ -198,6 +200,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
     a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
     a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles);
+    { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     rc = rb::launch_joint_gemm(1, tmW, tmGst, tmHst, a, grid, stream);
     if (rc) return rc;

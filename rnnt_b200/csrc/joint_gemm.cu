@@ -19,34 +19,44 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef RNNT_G_STAGES_A
+#define RNNT_G_STAGES_A 2
+#define RNNT_G_STAGES_B 4
+#endif
+
 namespace rb {
 
 namespace {
 
-constexpr int kStagesA = 4;
-constexpr int kStagesB = 4;
+// Shared-memory budget (227 KB): the W-tile (B operand) ring is the latency-critical one (TMA round trip ~1 us
+// vs 0.26 us of MMA work per 32 KB stage), the computed A operand only needs double buffering.
+template <int MODE> struct StagesA { static constexpr int value = MODE == 0 ? 4 : RNNT_G_STAGES_A; };
+template <int MODE> struct StagesB { static constexpr int value = MODE == 0 ? 4 : RNNT_G_STAGES_B; };
 constexpr int kBytesA = kTileM * kBK * 2;  // 16 KB
 constexpr int kBytesB = kBN * kBK * 2;     // 32 KB
 constexpr int kBytesG = kTileM * 64 * 2;   // 16 KB staging box for the gradient ring store
-constexpr int kNumThreads = 480;
-constexpr int kFirstEpiWarp = 2;
-constexpr int kFirstProdWarp = 6;
+constexpr int kNumThreads = 608;
+constexpr int kFirstEpiWarp = 2;      // warps 2-5: epilogue set 0 (accumulator 0), warps 6-9: set 1 (accumulator 1)
+constexpr int kNumEpiWarps = 8;
+constexpr int kFirstProdWarp = 10;
 constexpr int kNumProdWarps = 8;
-constexpr int kStoreWarp = 14;
+constexpr int kStoreWarp = 18;
 constexpr int kTmemCols = 512;
 
+template <int MODE>
 struct SmemLayout {
   // offsets from the 1024-aligned base
   static constexpr int b_ring = 0;
-  static constexpr int a_ring = b_ring + kStagesB * kBytesB;
-  static constexpr int g_stage = a_ring + kStagesA * kBytesA;
-  static constexpr int bars = g_stage + 2 * kBytesG;
+  static constexpr int a_ring = b_ring + StagesB<MODE>::value * kBytesB;
+  static constexpr int g_stage = a_ring + StagesA<MODE>::value * kBytesA;
+  static constexpr int xchg = g_stage + (MODE == 1 ? 4 * kBytesG : 0);     // F: set-1 -> set-0 softmax partials
+  static constexpr int bars = xchg + (MODE == 0 ? 2 * kTileM * 16 : 0);
   static constexpr int total = bars + 256;
 };
 
 }  // namespace
 
-size_t joint_gemm_smem_bytes() { return SmemLayout::total + 1024; }
+size_t joint_gemm_smem_bytes() { return SmemLayout<0>::total + 1024; }
 
 template <int MODE>  // 0 = forward (lse + gather), 1 = backward recompute (gradient ring)
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -55,16 +65,19 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  using SL = SmemLayout<MODE>;
+  constexpr int kStagesB = StagesB<MODE>::value;
+  constexpr int kStagesA = StagesA<MODE>::value;
 
-  const uint32_t b_ring = smem_base + SmemLayout::b_ring;
-  const uint32_t a_ring = smem_base + SmemLayout::a_ring;
-  const uint32_t g_stage = smem_base + SmemLayout::g_stage;
-  const uint32_t bars = smem_base + SmemLayout::bars;
+  const uint32_t b_ring = smem_base + SL::b_ring;
+  const uint32_t a_ring = smem_base + SL::a_ring;
+  const uint32_t g_stage = smem_base + SL::g_stage;
+  const uint32_t bars = smem_base + SL::bars;
   // barrier map (8 bytes each)
   const uint32_t b_full = bars, b_empty = bars + 8 * kStagesB;
   const uint32_t a_full = bars + 16 * kStagesB, a_empty = a_full + 8 * kStagesA;
   const uint32_t tmem_full = a_empty + 8 * kStagesA, tmem_empty = tmem_full + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SL::bars + 200);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +103,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       mbar_init(a_empty + 8 * s, MODE == 1 ? 2 : 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 4);
+    mbar_init(tmem_empty, kNumEpiWarps);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -155,15 +168,17 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         __syncwarp();
       }
     }
-  } else if (warp >= kFirstEpiWarp && warp < kFirstProdWarp) {
+  } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kNumEpiWarps) {
     // ===================================================================== epilogue
+    // Two epilogue sets work in parallel: set e drains accumulator e (256 columns) of every pass.
     const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
+    const int eset = (warp - kFirstEpiWarp) >> 2;
     const int row = lane_grp * 32 + lane;
     const int ti = row >> 3, ui = row & 7;
-    const int epi_tid = (warp - kFirstEpiWarp) * 32 + lane;
-    uint32_t pc = 0;
-    uint32_t box_count = 0;
-    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    const int set_tid = ((warp - kFirstEpiWarp) & 3) * 32 + lane;
+    float4* xchg = reinterpret_cast<float4*>(smem_gen + SL::xchg);
+    uint32_t pc = 0, box_count = 0, tcount = 0;
+    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x, ++tcount) {
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
       const int t = tc.t0 + ti, u = tc.u0 + ui;
       const bool valid = (t < tc.Tb) && (u <= tc.Ub);
@@ -171,7 +186,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       int tgt = -1;
       if (valid && u < tc.Ub) tgt = __ldg(p.targets + static_cast<long long>(tc.b) * p.tgt_ld + u);
       // F state (log2 units)
-      float m = -INFINITY, ssum = 0.f, x_tgt = 0.f, x_blank = 0.f;
+      float m = -INFINITY, ssum = 0.f, x_tgt = -INFINITY, x_blank = -INFINITY;
       // G state
       float gam = 0.f, eB = 0.f, eE = 0.f, lse2 = 1e30f, cbound = 0.f;
       if (MODE == 1 && valid) {
@@ -185,10 +200,11 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int nblk = min(2, nblk_total - pass * 2);
         mbar_wait(tmem_full, pc & 1);
         tc_fence_after();
-        for (int c32 = 0; c32 < nblk * (kBN / 32); ++c32) {
-          const int col0 = pass * 2 * kBN + c32 * 32;  // global column of v[0]
+        const int nchunk = ((p.dbg & 1) || eset >= nblk) ? 0 : (kBN / 32);
+        for (int c32 = 0; c32 < nchunk; ++c32) {
+          const int col0 = (pass * 2 + eset) * kBN + c32 * 32;  // global column of v[0]
           float v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + c32 * 32, v);
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + eset * kBN + c32 * 32, v);
           tmem_ld_wait();
           const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + col0);
 #pragma unroll
@@ -233,12 +249,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -cbound), cbound);
             }
-            // stage fp16 into the 128 x 64 swizzled box (two 32-column halves per box)
-            const uint32_t buf = g_stage + (box_count & 1) * kBytesG;
+            // stage fp16 into this set's 128 x 64 swizzled box (two 32-column halves per box)
+            const uint32_t buf = g_stage + (eset * 2 + (box_count & 1)) * kBytesG;
             if ((c32 & 1) == 0) {
               // the TMA store that last used this buffer (two boxes ago) must have finished reading it
-              if (epi_tid == 0) tma_store_wait_read<1>();
-              named_bar_sync(1, 128);
+              if (set_tid == 0) tma_store_wait_read<1>();
+              named_bar_sync(1 + eset, 128);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -254,9 +270,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             }
             if ((c32 & 1) == 1) {
               fence_proxy_async();
-              named_bar_sync(1, 128);
-              if (epi_tid == 0) {
-                tma_store_2d(&tmG, buf, pass * 2 * kBN + (c32 >> 1) * 64, ring_row0);
+              named_bar_sync(1 + eset, 128);
+              if (set_tid == 0) {
+                tma_store_2d(&tmG, buf, (pass * 2 + eset) * kBN + (c32 >> 1) * 64, ring_row0);
                 tma_store_commit();
               }
               ++box_count;
@@ -267,16 +283,25 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty);
       }
-      if (MODE == 0 && valid) {
-        const float l2 = m + lg2_approx(ssum);
-        p.lse[cell] = l2 * kLn2;
-        float2 o;
-        o.x = (x_blank - l2) * kLn2;
-        o.y = (tgt >= 0) ? (x_tgt - l2) * kLn2 : 0.f;
-        reinterpret_cast<float2*>(p.lp)[cell] = o;
+      if (MODE == 0) {
+        // combine the two sets' online-softmax partials: set 1 -> smem -> set 0 writes lp / lse
+        float4* slot = xchg + (tcount & 1) * kTileM + row;
+        if (eset == 1) *slot = make_float4(m, ssum, x_tgt, x_blank);
+        named_bar_sync(3, 256);
+        if (eset == 0 && valid && !(p.dbg & 1)) {
+          const float4 o = *slot;
+          const float mm = fmaxf(m, o.x);
+          const float stot = ssum * ex2_approx(m - mm) + o.y * ex2_approx(o.x - mm);
+          const float l2 = mm + lg2_approx(stot);
+          p.lse[cell] = l2 * kLn2;
+          float2 out;
+          out.x = (fmaxf(x_blank, o.w) - l2) * kLn2;
+          out.y = (tgt >= 0) ? (fmaxf(x_tgt, o.z) - l2) * kLn2 : 0.f;
+          reinterpret_cast<float2*>(p.lp)[cell] = out;
+        }
       }
     }
-    if (MODE == 1 && epi_tid == 0) tma_store_wait_all<0>();
+    if (MODE == 1 && set_tid == 0) tma_store_wait_all<0>();
   } else if (warp >= kFirstProdWarp && warp < kFirstProdWarp + kNumProdWarps) {
     // ===================================================================== A producers
     const int rg = warp - kFirstProdWarp;  // rows rg*16 .. rg*16+15  <->  t-rows 2rg, 2rg+1, all 8 u
@@ -317,6 +342,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
           mbar_wait(a_empty + 8 * s, ph ^ 1);
           const uint32_t stage = a_ring + s * kBytesA;
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
 #pragma unroll
@@ -372,7 +398,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
                       const JointArgs& args, int grid, cudaStream_t stream) {
   ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
-  const size_t smem = joint_gemm_smem_bytes();
+  const size_t smem = (mode == 0 ? SmemLayout<0>::total : SmemLayout<1>::total) + 1024;
   if (mode == 0) {
     RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     joint_gemm_kernel<0><<<grid, kNumThreads, smem, stream>>>(tmW, tmG, tmHr, args);

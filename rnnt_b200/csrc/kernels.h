@@ -30,6 +30,7 @@ struct JointArgs {
   const float* dcost;     // G: (B) or nullptr (only used to scale the clamp bound)
   const float* gscale;    // G: {S, 1/S} power-of-two gradient scale
   float clamp;            // G: <= 0 disables (torchaudio's clamp argument, rnnt/model.py:40 passes -1)
+  int dbg;                // diagnostics only (RNNT_B200_DBG): 1 = skip epilogue math, 2 = skip producer math
 };
 
 struct DhArgs {
