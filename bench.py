@@ -46,55 +46,61 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    """Samples SM clock, power and throttle reasons DURING the timed region (NVML every ~5 ms in a thread;
+    falls back to one nvidia-smi query if pynvml is unavailable)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.nvml = None
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                clk = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(
+                    n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((clk, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                 parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        if self.nvml is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable"])
+        self._stop.set()
+        self.thread.join(timeout=2)
+        if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(power),
-                    samples=len(sm), reasons=sorted(reasons))
+        n = self.nvml
+        bits = 0
+        for _, _, rs in self.samples:
+            bits |= rs
+        names = dict(hw_slowdown=getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     hw_thermal_slowdown=getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     sw_thermal_slowdown=getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     sw_power_cap=getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))
+        reasons = sorted(k for k, v in names.items() if bits & v)
+        return dict(sm_mhz=statistics.median(c for c, _, _ in self.samples), sm_max_mhz=float(self.max_sm),
+                    sm_min_mhz=min(c for c, _, _ in self.samples), power_w_max=max(p for _, p, _ in self.samples),
+                    samples=len(self.samples), reasons=reasons)
 
 
 def synth_inputs(torch, seed, device, b=B, t=T, u=U, pin=False):
@@ -159,8 +165,10 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from rnnt_b200 import _lib
+    import rnnt_b200.functional as RF
     from rnnt_b200.functional import joint_rnnt_loss
     from rnnt_b200.parallel import GradAllReducer
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,7 +193,8 @@ def run_gpu_arm(args):
         for k in ("enc", "pred", "W", "b"):
             s[k].grad = None
         loss = joint_rnnt_loss(s["enc"], s["pred"], s["W"], s["b"], s["targets"], s["T_len"], s["U_len"],
-                               blank=-1, clamp=-1, reduction="mean", validate=False)
+                               blank=-1, clamp=-1, reduction="mean", validate=False,
+                               skip_zero_tiles=not args.all_tiles)
         loss.backward()
         if world > 1:
             reducer.all_reduce_grads([s["W"].grad, s["b"].grad, pred_grad_stub], wait=True)
@@ -219,6 +228,28 @@ def run_gpu_arm(args):
     _lib.check(L.rnnt_b200_profile_end(fam_ms, fam_n), "profile_end")
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last.detach())
+    # secondary number: the same step with the backward forced over ALL lattice tiles (no zero-tile skipping)
+    dense_ms = None
+    if not args.all_tiles:
+        args.all_tiles = True
+        for i in range(2):
+            step(sets[i % n_sets])
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nd = max(2, args.steps // 2)
+        d0.record()
+        for i in range(nd):
+            step(sets[i % n_sets])
+        d1.record()
+        barrier()
+        dense_ms = d0.elapsed_time(d1) / nd
+        args.all_tiles = False
+    RF.COLLECT_BACKWARD_STATS = True
+    step(sets[0])
+    torch.cuda.synchronize()
+    active_tiles, total_tiles = RF.last_backward_stats()
+    RF.COLLECT_BACKWARD_STATS = False
+    bwd_frac = active_tiles / max(1, total_tiles)
 
     # ---- e2e: same step through the public API from pinned HOST buffers, result read back to host
     host = synth_inputs(torch, 4321 + rank, dev, pin=True)
@@ -247,10 +278,10 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks
-    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_s * 1e3, dense_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(times[0]), float(times[1])
+    ms_total, e2e_ms, dense_ms = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         peaks = load_peaks()
@@ -267,7 +298,10 @@ def run_gpu_arm(args):
             kern[nm] = dict(ms_per_step=per_step_ms, launches_per_step=fam_n[i] / args.steps,
                             share=per_step_ms / ms_step)
             if nm in ("joint_gemm_fwd", "joint_gemm_bwd", "dh_gemm", "dw_gemm"):
-                kern[nm]["tflops"] = gemm_flops_per_step_rank / (per_step_ms * 1e-3) / 1e12
+                # executed algorithmic FLOPs: the backward GEMMs only run over lattice tiles with non-zero gradients
+                frac = 1.0 if nm == "joint_gemm_fwd" else bwd_frac
+                kern[nm]["flops_per_step"] = gemm_flops_per_step_rank * frac
+                kern[nm]["tflops"] = gemm_flops_per_step_rank * frac / (per_step_ms * 1e-3) / 1e12
         gemms = {k: v for k, v in kern.items() if "tflops" in v}
         if not gemms:   # --no-kernel-profile: no per-kernel events were recorded
             gemms = {"whole_step": dict(ms_per_step=ms_step, launches_per_step=1.0,
@@ -277,24 +311,31 @@ def run_gpu_arm(args):
         achieved = gemms[dom]["tflops"]
         roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
                         frac=achieved / peaks["tflops"], traffic=None, peak_source=peaks["source"],
-                        flops_per_launch=gemm_flops_per_step_rank / launches_dom,
+                        flops_per_launch=gemms[dom].get("flops_per_step", gemm_flops_per_step_rank) / launches_dom,
                         avg_launch_ms=gemms[dom]["ms_per_step"] / launches_dom,
                         whole_step_frac_credited=(value / world) * 3 * FLOP_PER_CELL_GEMM / (peaks["tflops"] * 1e12),
                         kernels=kern)
         cpu_base, _ = time_cpu_reference(1, 1) if world == 1 and not args.no_cpu_baseline else (None, None)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp16",
                     data="synthetic",
                     config=dict(workload=f"joint+loss fused fwd+bwd, per-GPU B={B},T={T},U={U},H={H},V={V} "
                                          f"(BASELINE configs[1]); global batch {B * world}",
                                 parallelism=f"dp{world} by utterance, all-reduce of {V * H + V + PRED_GRAD_ELEMS} "
                                             "fp32 grads" if world > 1 else "single GPU",
-                                l2="3 rotating input sets (210 MB > 126 MB L2) + ~16 GB/step ring traffic",
+                                l2="3 rotating input sets (210 MB > 126 MB L2) + multi-GB/step ring traffic",
+                                operands="fp16 x fp16 -> fp32 (TMEM), fp32 elsewhere",
+                                backward_tiles=dict(active=active_tiles, total=total_tiles, fraction=bwd_frac,
+                                                    note="lattice tiles whose fp16 logit-gradients are all zero "
+                                                         "(occupancy < 2^-25) are skipped; --all-tiles disables"),
                                 loss=loss_val),
                     clocks=clocks,
                     e2e=dict(value=cells_step / (e2e_ms * 1e-3 / args.steps), unit=UNIT,
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(sum(fam_n)),
+                    all_tiles=(dict(ms_per_step=dense_ms, value=cells_step / (dense_ms * 1e-3), unit=UNIT,
+                                    note="same step, backward over every lattice tile (zero-gradient tiles not skipped)")
+                               if dense_ms else None),
                     roofline=roofline)
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
@@ -311,6 +352,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true", help="skip the per-kernel CUDA events")
+    ap.add_argument("--all-tiles", action="store_true",
+                    help="backward processes every lattice tile (also those whose fp16 gradients are all zero)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -54,13 +54,15 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
 
 /* Fused backward.  Replaces RnntLoss.backward + autograd through rnnt/joint.py:32-39.
  * dcost (B) = d loss / d cost_b (1/B for reduction="mean"); clamp <= 0 disables gradient clamping.
- * Outputs are overwritten: d_enc (B,T,H) contiguous, d_pred (B,U1,H), dW (V,H), dbias (V), all fp32. */
+ * Outputs are overwritten: d_enc (B,T,H) contiguous, d_pred (B,U1,H), dW (V,H), dbias (V), all fp32.
+ * Lattice tiles whose scaled logit-gradients are all below fp16 resolution (occupancy < 2^-25 of max|dcost|) are
+ * exactly zero in the gradient ring and are skipped; flags bit 0 = 1 disables the skipping (every tile is processed). */
 int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
                              const float* alpha, const float* beta, const float* dcost, float clamp, float* d_enc,
-                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, void* workspace,
-                             size_t workspace_bytes, void* stream);
+                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, int flags,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss on already materialised logits (B,T,U1,V) fp32 contiguous -- the literal torchaudio.functional.rnnt_loss
  * call of rnnt/model.py:35-41 for callers that hold logits (e.g. eval.py:76 style uses).  fwd writes costs and the
@@ -94,10 +96,11 @@ int rnnt_b200_profile_begin(void);
 int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
 
 /* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
- *   offsets[0] tile table (B+1 int32 prefix sums of tiles per utterance, then one status int)
+ *   offsets[0] tile table: B+1 int32 prefix sums of tiles per utterance, status, {S, 1/S} (fp32), n_active tiles
  *   offsets[1] W as fp16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
  *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] bf16
- *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16     offsets[6] total bytes.
+ *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16     offsets[6] total bytes
+ *   offsets[7] work list of active lattice tiles (int32).
  * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
 int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int64_t* offsets /*[8]*/,
                               int* Hp, int* Vp);

@@ -21,7 +21,7 @@ _SIGNATURES = {
                                  + [C.c_int] * 6 + [_f32p] * 5 + [_i32p, _ptr, C.c_size_t, _ptr]),
     "rnnt_b200_joint_loss_bwd": (C.c_int, [_f32p, C.c_int64, C.c_int64, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p]
                                  + [C.c_int] * 6 + [_f32p] * 5 + [C.c_float] + [_f32p] * 4
-                                 + [C.c_int64, _ptr, C.c_size_t, _ptr]),
+                                 + [C.c_int64, C.c_int, _ptr, C.c_size_t, _ptr]),
     "rnnt_b200_loss_dense_fwd": (C.c_int, [_f32p, _i32p, _i32p, _i32p] + [C.c_int] * 5 + [_f32p] * 5 + [_ptr]),
     "rnnt_b200_loss_dense_bwd": (C.c_int, [_f32p, _i32p, _i32p, _i32p] + [C.c_int] * 5 + [_f32p] * 5
                                  + [C.c_float, _f32p, _f32p, _ptr]),

@@ -17,7 +17,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t tile_off, wb, bias2, coef, g_ring, h_ring, total_fwd, total_bwd;
+  size_t tile_off, wb, bias2, coef, flags, tile_list, g_ring, h_ring, total_fwd, total_bwd;
   int Hp, Vp;
 };
 
@@ -26,11 +26,14 @@ WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles) {
   w.Hp = round_up(H, 64);
   w.Vp = round_up(V, 256);
   size_t off = 0;
-  w.tile_off = off; off = align_up(off + (static_cast<size_t>(B) + 4) * sizeof(int), 1024);   // + status, {S, 1/S}
+  w.tile_off = off; off = align_up(off + (static_cast<size_t>(B) + 6) * sizeof(int), 1024);   // + status, {S, 1/S}, n_active
   w.wb = off;       off = align_up(off + static_cast<size_t>(w.Vp) * w.Hp * 2, 1024);
   w.bias2 = off;    off = align_up(off + static_cast<size_t>(w.Vp) * 4, 1024);
   w.total_fwd = off;
   w.coef = off;     off = align_up(off + static_cast<size_t>(B) * T * U1 * 16, 1024);
+  const size_t max_tiles = static_cast<size_t>(B) * ((T + rb::kTileT - 1) / rb::kTileT) * ((U1 + rb::kTileU - 1) / rb::kTileU);
+  w.flags = off;    off = align_up(off + max_tiles, 1024);
+  w.tile_list = off; off = align_up(off + max_tiles * sizeof(int), 1024);
   const size_t ring_rows = static_cast<size_t>(ring_tiles) * kTileM;
   w.g_ring = off;   off = align_up(off + ring_rows * w.Vp * 2, 1024);
   w.h_ring = off;   off = align_up(off + ring_rows * w.Hp * 2, 1024);
@@ -76,7 +79,7 @@ int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_t
                               int* Vp) {
   const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
   offsets[0] = w.tile_off; offsets[1] = w.wb; offsets[2] = w.bias2; offsets[3] = w.coef;
-  offsets[4] = w.g_ring; offsets[5] = w.h_ring; offsets[6] = w.total_bwd; offsets[7] = w.total_fwd;
+  offsets[4] = w.g_ring; offsets[5] = w.h_ring; offsets[6] = w.total_bwd; offsets[7] = w.tile_list;
   if (Hp) *Hp = w.Hp;
   if (Vp) *Vp = w.Vp;
   return 0;
@@ -120,7 +123,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
   a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
   a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
-  a.tile_begin = 0; a.tile_cap = 0x3fffffff;
+  a.tile_begin = 0; a.tile_cap = 0x3fffffff; a.tile_list = nullptr; a.n_active = nullptr;
   { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
   const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
@@ -134,7 +137,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
                              const float* alpha, const float* beta, const float* dcost, float clamp, float* d_enc,
-                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, void* workspace,
+                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, int flags, void* workspace,
                              size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
@@ -166,6 +169,12 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
   rc = rb::launch_coef(lp, lse, alpha, beta, dcost, gscale, T_len, U_len, B, T, U1, coef, stream);
   if (rc) return rc;
+  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
+  int* n_active = tile_off + B + 4;
+  int* tile_list = reinterpret_cast<int*>(ws + w.tile_list);
+  rc = rb::launch_tile_activity(coef, T_len, U_len, tile_off, B, T, U1, max_tiles, (flags & 1) ? 1 : 0,
+                                reinterpret_cast<unsigned char*>(ws + w.flags), tile_list, n_active, stream);
+  if (rc) return rc;
 
   CUtensorMap tmW, tmWmn, tmGst, tmG256, tmHst, tmGmn, tmHmn;
   // W [Vp, Hp]: K-major boxes (64 k x 256 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
@@ -186,7 +195,6 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
 
   const int sms = rb::device_sm_count();
-  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
   const int64_t nchunks = (max_tiles + ring_tiles - 1) / ring_tiles;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int tile_begin = static_cast<int>(c * ring_tiles);
@@ -199,7 +207,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
     a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
     a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
-    a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles);
+    a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles); a.tile_list = tile_list; a.n_active = n_active;
     { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     rc = rb::launch_joint_gemm(1, tmW, tmGst, tmHst, a, grid, stream);
@@ -207,7 +215,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
 
     rb::DhArgs d{};
     d.enc = enc; d.enc_sb = enc_sb; d.enc_st = enc_st;
-    d.pred = pred; d.pred_sb = static_cast<long long>(U1) * H; d.pred_su = H; d.gscale = gscale;
+    d.pred = pred; d.pred_sb = static_cast<long long>(U1) * H; d.pred_su = H; d.gscale = gscale; d.tile_list = tile_list; d.n_active = n_active;
     d.T_len = T_len; d.U_len = U_len; d.tile_off = tile_off;
     d.B = B; d.T = T; d.U1 = U1; d.H = H; d.Hp = w.Hp; d.Vp = w.Vp;
     d.tile_begin = tile_begin; d.tile_cap = static_cast<int>(ring_tiles);
@@ -217,7 +225,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     if (rc) return rc;
 
     rb::DwArgs g{};
-    g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
+    g.n_active = n_active; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
     g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW; g.db = dbias; g.gscale = gscale;
     const int out_tiles = (w.Vp / kTileM) * ((((w.Hp + 255) / 256) + 1) / 2);
     const int64_t kchunks = chunk_tiles * 2;

@@ -43,8 +43,8 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = __ldg(p.tile_off + p.B);
-  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
+  const int total_tiles = __ldg(p.n_active);
+  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots
   const int ntiles = max(0, tile_end - p.tile_begin);
   const int ncb = (ntiles + 1) / 2;                 // cell blocks of 2 lattice tiles (256 ring rows)
   const int nhb = (p.Hp + 127) / 128;               // hidden blocks of 128
@@ -120,9 +120,9 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        const int tile = p.tile_begin + cb * 2 + half;
-        if (tile >= tile_end) break;            // uniform
-        const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
+        const int slot = p.tile_begin + cb * 2 + half;
+        if (slot >= tile_end) break;            // uniform
+        const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, __ldg(p.tile_list + slot));
         float pv[8], su[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

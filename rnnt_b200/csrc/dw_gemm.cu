@@ -40,7 +40,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = __ldg(p.tile_off + p.B);
+  const int total_tiles = __ldg(p.n_active);
   const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
   const int nkc = max(0, tile_end - p.tile_begin) * (kTileM / kBK);   // 64-row K chunks in this ring chunk
 

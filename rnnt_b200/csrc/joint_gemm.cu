@@ -82,8 +82,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int total_tiles = __ldg(p.tile_off + p.B);
-  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
+  const int total_tiles = p.n_active ? __ldg(p.n_active) : __ldg(p.tile_off + p.B);
+  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots [tile_begin, tile_end)
   const int nk = p.Hp / kBK;
   const int nblk_total = p.Vp / kBN;
   const int npass = (nblk_total + 1) / 2;
@@ -119,7 +119,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // ===================================================================== TMA producer (W tiles)
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+      for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
         for (int pass = 0; pass < npass; ++pass) {
           const int nblk = min(2, nblk_total - pass * 2);
           for (int kc = 0; kc < nk; ++kc) {
@@ -137,7 +137,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // ===================================================================== MMA issuer
     constexpr uint32_t idesc = make_idesc(kTileM, kBN, 0, 0, kFmtF16, kFmtF16);
     uint32_t ita = 0, itb = 0, pc = 0;
-    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
       for (int pass = 0; pass < npass; ++pass, ++pc) {
         const int nblk = min(2, nblk_total - pass * 2);
         mbar_wait(tmem_empty, (pc & 1) ^ 1);
@@ -178,7 +178,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int set_tid = ((warp - kFirstEpiWarp) & 3) * 32 + lane;
     float4* xchg = reinterpret_cast<float4*>(smem_gen + SL::xchg);
     uint32_t pc = 0, box_count = 0, tcount = 0;
-    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x, ++tcount) {
+    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++tcount) {
+      const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
       const int t = tc.t0 + ti, u = tc.u0 + ui;
       const bool valid = (t < tc.Tb) && (u <= tc.Ub);
@@ -194,7 +195,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         gam = c4.x; eB = c4.y; eE = c4.z; lse2 = c4.w * kLog2e;
         if (p.clamp > 0.f) cbound = p.clamp * fabsf(p.dcost ? __ldg(p.dcost + tc.b) : 1.f) * __ldg(p.gscale);
       }
-      const int ring_row0 = (tile - p.tile_begin) * kTileM;
+      const int ring_row0 = (slot - p.tile_begin) * kTileM;
 
       for (int pass = 0; pass < npass; ++pass, ++pc) {
         const int nblk = min(2, nblk_total - pass * 2);
@@ -307,7 +308,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int rg = warp - kFirstProdWarp;  // rows rg*16 .. rg*16+15  <->  t-rows 2rg, 2rg+1, all 8 u
     const int kp = lane;                   // column pair within the 64-wide K chunk
     uint32_t it = 0;
-    for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
+      const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
       const float* e_ptr[2];
       const float* p_ptr[8];
@@ -368,8 +370,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // ===================================================================== hidden-ring store (G mode)
     if (MODE == 1 && lane == 0) {
       uint32_t it = 0;
-      for (int tile = p.tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
-        const int ring_row0 = (tile - p.tile_begin) * kTileM;
+      for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
+        const int ring_row0 = (slot - p.tile_begin) * kTileM;
         for (int pass = 0; pass < npass; ++pass) {
           for (int kc = 0; kc < nk; ++kc, ++it) {
             const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;

@@ -23,7 +23,9 @@ struct JointArgs {
   const int* U_len;
   const int* tile_off;    // [B+1] prefix sum of tiles per utterance; tile_off[B] = total
   int B, T, U1, H, Hp, V, Vp, blank;
-  int tile_begin, tile_cap;   // process tiles [tile_begin, min(total, tile_begin + tile_cap))
+  int tile_begin, tile_cap;   // process work-list slots [tile_begin, min(count, tile_begin + tile_cap))
+  const int* tile_list;   // G: slot -> lattice tile (active tiles only); nullptr (F) = identity over all tiles
+  const int* n_active;    // G: number of slots in tile_list
   float* lp;              // F: (B,T,U1,2) log-probs (blank, label)
   float* lse;             // F: (B,T,U1) log-sum-exp of the logits (natural log)
   const float4* coef;     // G: (B,T,U1) (gamma*dc*S, eB*dc*S, eE*dc*S, lse)
@@ -39,6 +41,8 @@ struct DhArgs {
   const float* pred;      // (B,U1,H)
   long long pred_sb, pred_su;
   const float* gscale;    // {S, 1/S}
+  const int* tile_list;   // slot -> lattice tile; ring row block i holds tile_list[tile_begin + i]
+  const int* n_active;
   const int* T_len;
   const int* U_len;
   const int* tile_off;
@@ -49,6 +53,7 @@ struct DhArgs {
 };
 
 struct DwArgs {
+  const int* n_active;   // number of work-list slots (ring rows of this chunk = slots in range * 128)
   const int* tile_off;
   int B, H, Hp, V, Vp;
   int tile_begin, tile_cap;
@@ -75,6 +80,9 @@ int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, i
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
                 const float* gscale, const int* T_len, const int* U_len, int B, int T, int U1, float4* coef,
                 cudaStream_t stream);
+int launch_tile_activity(const float4* coef, const int* T_len, const int* U_len, const int* tile_off, int B, int T,
+                         int U1, long long max_tiles, int dense, unsigned char* flags, int* tile_list, int* n_active,
+                         cudaStream_t stream);
 int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
                           int B, int T, int U1, int V, int blank, float* lp, float* lse, cudaStream_t stream);
 int launch_dense_grads(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,

@@ -16,6 +16,19 @@ from . import _lib
 
 _DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(1 << 30)))
 
+# Optional bookkeeping for bench.py / tests: when enabled, every fused backward leaves a 2-element device tensor
+# (active lattice tiles, total lattice tiles) here.  Off by default (costs two tiny copies per step).
+COLLECT_BACKWARD_STATS = False
+_last_backward_stats = None
+
+
+def last_backward_stats():
+    """(active_tiles, total_tiles) of the most recent fused backward, or None.  Synchronises."""
+    if _last_backward_stats is None:
+        return None
+    a, t = _last_backward_stats.tolist()
+    return int(a), int(t)
+
 
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
@@ -69,7 +82,8 @@ class _FusedJointLoss(torch.autograd.Function):
     """costs[B] = transducer loss of joint_ln(tanh(enc + pred)); residuals are 5 lattice-sized fp32 tensors."""
 
     @staticmethod
-    def forward(ctx, enc, pred, weight, bias, targets, logit_lengths, target_lengths, blank, clamp, ring_bytes):
+    def forward(ctx, enc, pred, weight, bias, targets, logit_lengths, target_lengths, blank, clamp, ring_bytes,
+                skip_zero_tiles=True):
         L = _lib.lib()
         B, T, H = enc.shape
         U1 = pred.shape[1]
@@ -95,6 +109,7 @@ class _FusedJointLoss(torch.autograd.Function):
         ctx.save_for_backward(enc_c, pred_c, weight_c, bias_c, targets, logit_lengths, target_lengths,
                               lp, lse, alpha, beta)
         ctx.blank, ctx.clamp, ctx.ring_bytes = blank, clamp, ring_bytes
+        ctx.flags = 0 if skip_zero_tiles else 1
         ctx.mark_non_differentiable(lp, lse, alpha, beta)
         return costs, lp, lse, alpha, beta
 
@@ -120,9 +135,12 @@ class _FusedJointLoss(torch.autograd.Function):
                 targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(), B, T, U1, H, V, ctx.blank,
                 lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(), dcost.data_ptr(),
                 float(ctx.clamp), d_enc.data_ptr(), d_pred.data_ptr(), dW.data_ptr(), db.data_ptr(), ring_tiles,
-                ws.data_ptr(), bwd_bytes, _stream_ptr(dev)), "joint_loss_bwd")
-        ctx.last_workspace = ws   # kept alive for tests that inspect the rings
-        return d_enc, d_pred, dW, db, None, None, None, None, None, None
+                ctx.flags, ws.data_ptr(), bwd_bytes, _stream_ptr(dev)), "joint_loss_bwd")
+        if COLLECT_BACKWARD_STATS:
+            global _last_backward_stats
+            meta = ws[: (B + 5) * 4].view(torch.int32)     # tile table region starts at offset 0
+            _last_backward_stats = torch.stack([meta[B + 4], meta[B]])
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None
 
 
 def _reduce(costs, reduction):
@@ -137,13 +155,16 @@ def _reduce(costs, reduction):
 
 def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths, blank: int = -1,
                     clamp: float = -1, reduction: str = "mean", validate: bool = True,
-                    ring_bytes: Optional[int] = None, return_residuals: bool = False):
+                    ring_bytes: Optional[int] = None, return_residuals: bool = False,
+                    skip_zero_tiles: bool = True):
     """Fused replacement for `joint_ln(tanh(a.unsqueeze(2) + p.unsqueeze(1)))` (rnnt/joint.py:32-39) followed by
     `torchaudio.functional.rnnt_loss(..., blank, clamp, reduction)` (rnnt/model.py:35-41).
 
     audio_frame (B,T,H) and text_frame (B,U+1,H) are the (already projected) joint inputs; weight (V,H) / bias (V)
     are joint_ln's parameters.  Per-utterance costs when reduction="none".  validate=True performs torchaudio's
     host-side length checks (one device sync, as the reference does); pass False on the hot loop.
+    skip_zero_tiles=False makes the backward process every lattice tile, including those whose fp16 logit-gradients
+    are identically zero (same result, more work).
     """
     _require_cuda(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths)
     if audio_frame.dtype != torch.float32 or text_frame.dtype != torch.float32:
@@ -158,7 +179,7 @@ def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_length
         _validate_lengths(audio_frame.shape[1], text_frame.shape[1], logit_lengths, target_lengths)
     costs, lp, lse, alpha, beta = _FusedJointLoss.apply(audio_frame, text_frame, weight.float(), bias.float(),
                                                         targets, logit_lengths, target_lengths, int(blank),
-                                                        float(clamp), ring_bytes)
+                                                        float(clamp), ring_bytes, bool(skip_zero_tiles))
     out = _reduce(costs, reduction)
     if return_residuals:
         return out, dict(lp=lp, lse=lse, alpha=alpha, beta=beta)

@@ -46,7 +46,7 @@ def _fwd_bwd(B, T, U, H, V, ragged, ring_tiles=None, check_rings=True):
     inp = make_inputs(B, T, U, H, V, ragged=ragged)
     ref = torch_reference(inp)
     refq = torch_reference(inp, emulate_bf16=True)
-    out = fused_raw(inp, ring_tiles=ring_tiles)
+    out = fused_raw(inp, ring_tiles=ring_tiles, flags=int(os.environ.get('BWD_FLAGS', '0')))
     tag = f"B{B} T{T} U{U} H{H} V{V} ragged={ragged} ring={out['ring_tiles']}"
     print(tag, "status", out["status"])
     print("  costs mine", out["costs"][:4].tolist(), "ref", ref["costs"][:4].tolist())
@@ -64,7 +64,8 @@ def _fwd_bwd(B, T, U, H, V, ragged, ring_tiles=None, check_rings=True):
     if check_rings and out["ring_tiles"] * 128 <= 200000:
         g_ring, h_ring, S = ring_views(out)
         print('  gradient scale S =', S)
-        rows = tile_rows(inp["T_len"], inp["U_len"])
+        rows = tile_rows(inp["T_len"], inp["U_len"], out)
+        print("  active tiles", out["active_tiles"], "of", out["total_tiles"])
         n = min(len(rows), g_ring.shape[0])
         bi = torch.tensor([r[0] for r in rows[:n]], device="cuda")
         ti = torch.tensor([min(r[1], T - 1) for r in rows[:n]], device="cuda")

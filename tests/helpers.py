@@ -27,7 +27,7 @@ def make_inputs(B, T, U, H, V, seed=1234, ragged=False, device="cuda", scale=1.0
     return dict(enc=to(enc), pred=to(pred), W=to(W), b=to(b), targets=to(targets), T_len=to(T_len), U_len=to(U_len))
 
 
-def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0):
+def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0):
     """Call the C-ABI forward + backward directly; returns outputs plus the raw workspace and its layout."""
     from rnnt_b200 import _lib
     from rnnt_b200.functional import _stream_ptr, pick_ring_tiles
@@ -62,10 +62,11 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0):
         targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["lp"].data_ptr(),
         out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(), dcost.data_ptr(), float(clamp),
         out["d_enc"].data_ptr(), out["d_pred"].data_ptr(), out["dW"].data_ptr(), out["db"].data_ptr(),
-        ring_tiles, ws.data_ptr(), ws.numel(), st), "bwd")
+        ring_tiles, flags, ws.data_ptr(), ws.numel(), st), "bwd")
     torch.cuda.synchronize()
+    meta = ws[int(offs[0]): int(offs[0]) + (B + 5) * 4].view(torch.int32)
     out.update(ws=ws, offs=[int(x) for x in offs], Hp=hp.value, Vp=vp.value, ring_tiles=ring_tiles,
-               status=int(status.item()))
+               status=int(status.item()), total_tiles=int(meta[B]), active_tiles=int(meta[B + 4]))
     return out
 
 
@@ -79,9 +80,17 @@ def ring_views(out):
     return g, h, float(scale[0])
 
 
-def tile_rows(T_len, U_len):
-    """For every ring row of the (single-chunk) backward: (b, t, u, valid).  Mirrors the kernels' tile map."""
+def tile_rows(T_len, U_len, out=None):
+    """For every ring row of the (single-chunk) backward: (b, t, u, valid).  Mirrors the kernels' tile map; with
+    `out` (result of fused_raw) only the tiles of the backward's work list are returned, in ring order."""
     rows = []
+    if out is not None:
+        n = out["active_tiles"]
+        lst = out["ws"][out["offs"][7]: out["offs"][7] + n * 4].view(torch.int32).tolist()
+        allrows = tile_rows(T_len, U_len)
+        for tile in lst:
+            rows.extend(allrows[tile * 128:(tile + 1) * 128])
+        return rows
     for b, (Tb, Ub) in enumerate(zip(T_len.tolist(), U_len.tolist())):
         nt, nu = (Tb + 15) // 16, (Ub + 1 + 7) // 8
         for it in range(nt):

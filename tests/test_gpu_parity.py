@@ -66,6 +66,20 @@ def test_multi_chunk_backward_equals_single_chunk():
         assert rel_err(many[k], one[k])[0] < 1e-5, k
 
 
+def test_zero_tile_skipping_is_exact():
+    """Tiles dropped from the backward hold only zeros in the fp16 gradient ring: results equal the all-tiles run."""
+    inp = make_inputs(2, 160, 40, 128, 512, ragged=True, seed=17)
+    dense = fused_raw(inp, flags=1)
+    sparse = fused_raw(inp, flags=0)
+    assert dense["active_tiles"] == dense["total_tiles"]
+    assert 0 < sparse["active_tiles"] < sparse["total_tiles"]
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert rel_err(sparse[k], dense[k])[0] < 2e-6, (k, rel_err(sparse[k], dense[k]))
+    ref = torch_reference(inp)
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert rel_err(sparse[k], ref[k])[0] <= GRAD_TOL_FP32, k
+
+
 def test_padded_cells_have_zero_gradient_and_edge_lengths():
     # U_b = 0 (pure blank path), T_b = 1, and a fully ragged batch; padded frames / labels get exactly zero grads
     inp = make_inputs(4, 18, 6, 64, 256, ragged=True, seed=7)
