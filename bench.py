@@ -309,8 +309,13 @@ def run_gpu_arm(args):
         dom = max(gemms, key=lambda k: gemms[k]["ms_per_step"])
         launches_dom = gemms[dom]["launches_per_step"]
         achieved = gemms[dom]["tflops"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):     # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
         roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                        frac=achieved / peaks["tflops"], traffic=None, peak_source=peaks["source"],
+                        frac=achieved / peaks["tflops"], traffic=traffic, peak_source=peaks["source"],
                         flops_per_launch=gemms[dom].get("flops_per_step", gemm_flops_per_step_rank) / launches_dom,
                         avg_launch_ms=gemms[dom]["ms_per_step"] / launches_dom,
                         whole_step_frac_credited=(value / world) * 3 * FLOP_PER_CELL_GEMM / (peaks["tflops"] * 1e12),

@@ -271,7 +271,14 @@ def lattice(lp, logit_lengths, target_lengths):
     return alpha, beta, costs
 
 
-def joint_argmax(audio_rows, text_rows, weight, bias, return_margin: bool = False):
+def joint_argmax_scratch(N: int, V: int, device):
+    """Reusable scratch for `joint_argmax(..., scratch=...)` (lets a decode loop run allocation-free)."""
+    n = max(1, _lib.lib().rnnt_b200_joint_argmax_scratch_bytes(N, V))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def joint_argmax(audio_rows, text_rows, weight, bias, return_margin: bool = False, out=None, margin_out=None,
+                 scratch=None):
     """tokens[n] = argmax(joint.single_forward(audio_rows[n], text_rows[n])) in fp32 (rnnt/model.py:110-113)."""
     _require_cuda(audio_rows, text_rows, weight, bias)
     N, H = audio_rows.shape
@@ -283,10 +290,13 @@ def joint_argmax(audio_rows, text_rows, weight, bias, return_margin: bool = Fals
     weight = weight.contiguous()
     bias = bias.contiguous()
     dev = audio_rows.device
-    tokens = torch.empty(N, dtype=torch.int32, device=dev)
-    margin = torch.empty(N, dtype=torch.float32, device=dev) if return_margin else None
+    tokens = torch.empty(N, dtype=torch.int32, device=dev) if out is None else out
+    margin = None
+    if return_margin:
+        margin = torch.empty(N, dtype=torch.float32, device=dev) if margin_out is None else margin_out
     L = _lib.lib()
-    scratch = torch.empty(max(1, L.rnnt_b200_joint_argmax_scratch_bytes(N, V)), dtype=torch.uint8, device=dev)
+    if scratch is None:
+        scratch = torch.empty(max(1, L.rnnt_b200_joint_argmax_scratch_bytes(N, V)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.rnnt_b200_joint_argmax(
             audio_rows.data_ptr(), audio_rows.stride(0), text_rows.data_ptr(), text_rows.stride(0),

@@ -81,8 +81,8 @@ class JointNetwork(torch.nn.Module):
                                logit_lengths, target_lengths, blank=blank, clamp=clamp, reduction=reduction,
                                validate=validate)
 
-    def argmax_step(self, audio_rows, text_rows, return_margin: bool = False):
+    def argmax_step(self, audio_rows, text_rows, return_margin: bool = False, **kw):
         """argmax(single_forward(audio_rows, text_rows), -1) for a batch of rows in fp32 (decode step)."""
         from .functional import joint_argmax
         audio_rows, text_rows = self._project(audio_rows, text_rows)
-        return joint_argmax(audio_rows, text_rows, self.joint_ln.weight, self.joint_ln.bias, return_margin)
+        return joint_argmax(audio_rows, text_rows, self.joint_ln.weight, self.joint_ln.bias, return_margin, **kw)

@@ -56,3 +56,39 @@ class ConvPredictor(torch.nn.Module):
         full-history re-run (rnnt/model.py:122-123) yields at the last position; shorter histories are passed
         whole so the left zero padding matches."""
         return self.forward(windows)[:, -1, :]
+
+
+class ConvPredictorStepper:
+    """Incremental evaluation of ConvPredictor for greedy decode: one new token per utterance per call.
+
+    The predictor is causal with a receptive field of 7 tokens, so the reference's full-history re-run
+    (rnnt/model.py:119-123) equals a streaming update that keeps, per utterance, the last 2 layer-normed embeddings
+    (conv1, k=3) and the last 4 conv1 outputs (conv2, k=5).  Zero-initialised state IS the left zero padding of
+    rnnt/causalconv.py:29, so short histories need no special case.  All tensors stay on the device; `advance`
+    updates only the rows selected by `emit`.
+    """
+
+    def __init__(self, predictor: ConvPredictor, batch: int, device):
+        p = predictor
+        E = p.embedding.embedding_dim
+        self.p = p
+        # conv weight (Co, Ci, k) -> (Co, k*Ci) matching the [oldest ... newest] concatenation of the taps
+        self.w1 = p.conv1.conv.weight.detach().permute(0, 2, 1).reshape(E, -1).contiguous()
+        self.w2 = p.conv2.conv.weight.detach().permute(0, 2, 1).reshape(E, -1).contiguous()
+        self.b1 = p.conv1.conv.bias.detach()
+        self.b2 = p.conv2.conv.bias.detach()
+        self.xs = torch.zeros(batch, 2, E, device=device)
+        self.ys = torch.zeros(batch, 4, E, device=device)
+
+    @torch.no_grad()
+    def advance(self, tokens, emit):
+        """tokens (B,) int64, emit (B,) bool -> predictor features (B, D) for rows with emit (others: garbage)."""
+        p = self.p
+        x = p.input_layer_norm(p.embedding(tokens))                                   # (B,E)
+        y = F.gelu(F.linear(torch.cat([self.xs.flatten(1), x], 1), self.w1, self.b1))   # conv1 at the new position
+        z = F.gelu(F.linear(torch.cat([self.ys.flatten(1), y], 1), self.w2, self.b2))   # conv2 at the new position
+        out = p.output_layer_norm(p.linear(z))
+        m = emit.view(-1, 1, 1)
+        self.xs.copy_(torch.where(m, torch.cat([self.xs[:, 1:], x[:, None]], 1), self.xs))
+        self.ys.copy_(torch.where(m, torch.cat([self.ys[:, 1:], y[:, None]], 1), self.ys))
+        return out

@@ -99,6 +99,28 @@ def test_conv_predictor_mirror_and_window_equivalence():
         torch.testing.assert_close(p.last_step(win), full[:, n - 1], rtol=1e-5, atol=1e-6)
 
 
+def test_incremental_predictor_equals_full_rerun():
+    """ConvPredictorStepper (device-side decode state) reproduces the reference's full-history re-run exactly."""
+    import rnnt_b200
+    from rnnt_b200.predictor import ConvPredictorStepper
+    torch.manual_seed(1)
+    p = rnnt_b200.ConvPredictor(40, 24, 16, 0.3).eval()
+    ids = torch.randint(0, 40, (4, 11))
+    full = p(ids)
+    st = ConvPredictorStepper(p, 4, "cpu")
+    everyone = torch.ones(4, dtype=torch.bool)
+    for i in range(11):
+        torch.testing.assert_close(st.advance(ids[:, i], everyone), full[:, i], rtol=1e-5, atol=1e-5)
+    # rows that do not emit keep their state
+    st2 = ConvPredictorStepper(p, 4, "cpu")
+    mask = torch.tensor([True, False, True, False])
+    st2.advance(ids[:, 0], everyone)
+    st2.advance(ids[:, 1], mask)
+    out = st2.advance(ids[:, 2], everyone)
+    torch.testing.assert_close(out[0], full[0, 2], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out[1], p(ids[1:2, [0, 2]])[0, 1], rtol=1e-5, atol=1e-5)
+
+
 def test_ring_chunking_and_sharding_helpers():
     from rnnt_b200.functional import pick_ring_tiles
     from rnnt_b200.parallel import balanced_assignment, shard_bounds

@@ -257,6 +257,15 @@ def test_greedy_decode_matches_reference_golden(golden_dir):
         want = g["tok_flat"][off:off + n].tolist()
         off += n
         assert got[i] == want, (i, min(margins[i]))
+    # the eager (no CUDA graph) device loop and the host-driven loop agree with it
+    assert model.greedy_decode_features(feats, torch.from_numpy(g["T_len"]), max_length=int(g["max_length"]),
+                                        use_cuda_graph=False) == got
+    assert model._greedy_decode_features_hostloop(feats, torch.from_numpy(g["T_len"]),
+                                                  max_length=int(g["max_length"])) == got
+    # reference-signature entry: batch of one through an (identity) encoder, list[int] out
+    one = model.greedy_decode(feats[:1, : int(g["T_len"][0])].permute(0, 2, 1), torch.tensor([int(g["T_len"][0])]),
+                              max_length=int(g["max_length"]))
+    assert one == got[0]
 
 
 def test_decode_step_full_width_vs_fp64():
