@@ -62,46 +62,39 @@ __global__ void convert_weights_kernel(const float* __restrict__ W, const float*
   }
 }
 
+// log(exp(a) + exp(b)) on the critical path of the wavefront: two MUFU ops (ex2, lg2; relative error ~2^-22 on a
+// term bounded by ln 2) instead of the ~50-instruction expf/log1pf pair.
 __device__ __forceinline__ float lse2f(float a, float b) {
   const float m = fmaxf(a, b);
   if (m == -INFINITY) return -INFINITY;
-  return m + log1pf(expf(fminf(a, b) - m));
+  const float d = fminf(a, b) - m;                        // <= 0, may be -inf
+  return fmaf(lg2_approx(1.f + ex2_approx(d * kLog2e)), kLn2, m);
 }
 
 constexpr int kPre = 8;
 
-__global__ void lattice_kernel(const float* __restrict__ lp, const int* __restrict__ T_len,
-                               const int* __restrict__ U_len, int T, int U1, float* __restrict__ alpha,
-                               float* __restrict__ beta, float* __restrict__ costs) {
-  extern __shared__ float sh[];   // 2 x (blockDim.x + 2)
-  const int b = blockIdx.x;
-  const bool is_beta = blockIdx.y == 1;
-  const int u = threadIdx.x;
-  const int Tb = max(1, min(T_len[b], T)), Ub = max(0, min(U_len[b], U1 - 1));
+// Thread u owns lattice column u.  In step s it sits at t = s - u (alpha) or t = Tb-1 - (s - (Ub - u)) (beta), i.e.
+// it is active for the Tb consecutive steps starting at s0 = u (alpha) / Ub - u (beta) and walks its column with a
+// constant pointer stride, so the per-step work is: one prefetched float2, one smem read, one LSE, two stores.
+template <bool BETA>
+__device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, float* __restrict__ out,
+                                             float* __restrict__ costs_b, int Tb, int Ub, int U1, int u, float* sh0,
+                                             float* sh1) {
   const int ndiag = Tb + Ub;
-  const int stride = blockDim.x + 2;
-  float* sh0 = sh + 1;             // sh0[-1] and sh0[blockDim.x] are -inf guards
-  float* sh1 = sh + stride + 1;
-  if (u == 0) {
-    sh0[-1] = -INFINITY; sh1[-1] = -INFINITY;
-    sh0[blockDim.x] = -INFINITY; sh1[blockDim.x] = -INFINITY;
-  }
-  sh0[u] = -INFINITY;
-  sh1[u] = -INFINITY;
-  __syncthreads();
-  const float2* lp2 = reinterpret_cast<const float2*>(lp) + static_cast<long long>(b) * T * U1;
-  float* out = (is_beta ? beta : alpha) + static_cast<long long>(b) * T * U1;
   const bool col_ok = u <= Ub;
+  const int s0 = BETA ? (Ub - u) : u;                       // first active step of this thread
+  const long long step = BETA ? -static_cast<long long>(U1) : U1;
+  const long long first = (BETA ? static_cast<long long>(Tb - 1) * U1 : 0) + u;
+  const float2* src = lp2 + first;                           // cell visited at local step 0
+  float* dst = out + first;
+  const int nb = BETA ? u + 1 : u - 1;                       // neighbour column feeding this one
 
   float2 cur[kPre], nxt[kPre];
-  auto fetch = [&](int g, float2 (&dst)[kPre]) {
+  auto fetch = [&](int g, float2 (&d)[kPre]) {
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
-      const int s = g * kPre + i;                       // step index 0..ndiag-1
-      const int n = is_beta ? (ndiag - 1 - s) : s;      // diagonal
-      const int t = n - u;
-      dst[i] = (s < ndiag && col_ok && t >= 0 && t < Tb) ? __ldg(lp2 + static_cast<long long>(t) * U1 + u)
-                                                          : make_float2(0.f, 0.f);
+      const int rel = g * kPre + i - s0;
+      d[i] = (col_ok && rel >= 0 && rel < Tb) ? __ldg(src + rel * step) : make_float2(0.f, 0.f);
     }
   };
   const int ngroups = (ndiag + kPre - 1) / kPre;
@@ -113,35 +106,56 @@ __global__ void lattice_kernel(const float* __restrict__ lp, const int* __restri
     for (int i = 0; i < kPre; ++i) {
       const int s = g * kPre + i;
       if (s < ndiag) {    // uniform over the block
-        const int n = is_beta ? (ndiag - 1 - s) : s;
-        const int t = n - u;
+        const int rel = s - s0;
         float* wr = (s & 1) ? sh1 : sh0;
         const float* rd = (s & 1) ? sh0 : sh1;
-        if (col_ok && t >= 0 && t < Tb) {
+        float pub = -INFINITY;
+        if (col_ok && rel >= 0 && rel < Tb) {
           const float lpB = cur[i].x, lpE = cur[i].y;
+          const float side = rd[nb];                     // guards hold -inf at columns -1 and blockDim.x
           float val;
-          if (!is_beta) {
-            if (n == 0) val = 0.f;
-            else val = lse2f(t > 0 ? own : -INFINITY, u > 0 ? rd[u - 1] : -INFINITY);
-            own = val + lpB;                       // feeds alpha(t+1,u)
-            wr[u] = (u < Ub) ? val + lpE : -INFINITY;   // feeds alpha(t,u+1)
+          if (!BETA) {
+            val = (s == 0) ? 0.f : lse2f(own, side);     // own = -inf at t = 0, side = -inf at u = 0
+            own = val + lpB;                             // feeds alpha(t+1,u)
+            pub = (u < Ub) ? val + lpE : -INFINITY;      // feeds alpha(t,u+1)
           } else {
-            if (t == Tb - 1 && u == Ub) val = lpB;
-            else val = lse2f(t < Tb - 1 ? own + lpB : -INFINITY, u < Ub ? rd[u + 1] + lpE : -INFINITY);
+            val = (s == 0) ? lpB : lse2f(own + lpB, (u < Ub) ? side + lpE : -INFINITY);   // own = -inf at t = Tb-1
             own = val;
-            wr[u] = val;
+            pub = val;
+            if (s == ndiag - 1) *costs_b = -val;
           }
-          out[static_cast<long long>(t) * U1 + u] = val;
-          if (is_beta && n == 0) costs[b] = -val;
-        } else {
-          wr[u] = -INFINITY;
+          dst[rel * step] = val;
         }
+        wr[u] = pub;
         __syncthreads();
       }
     }
 #pragma unroll
     for (int i = 0; i < kPre; ++i) cur[i] = nxt[i];
   }
+}
+
+__global__ void lattice_kernel(const float* __restrict__ lp, const int* __restrict__ T_len,
+                               const int* __restrict__ U_len, int T, int U1, float* __restrict__ alpha,
+                               float* __restrict__ beta, float* __restrict__ costs) {
+  extern __shared__ float sh[];   // 2 x (blockDim.x + 2)
+  const int b = blockIdx.x;
+  const int u = threadIdx.x;
+  const int Tb = max(1, min(T_len[b], T)), Ub = max(0, min(U_len[b], U1 - 1));
+  const int stride = blockDim.x + 2;
+  float* sh0 = sh + 1;             // sh0[-1] and sh0[blockDim.x] are -inf guards
+  float* sh1 = sh + stride + 1;
+  if (u == 0) {
+    sh0[-1] = -INFINITY; sh1[-1] = -INFINITY;
+    sh0[blockDim.x] = -INFINITY; sh1[blockDim.x] = -INFINITY;
+  }
+  sh0[u] = -INFINITY;
+  sh1[u] = -INFINITY;
+  __syncthreads();
+  const long long off = static_cast<long long>(b) * T * U1;
+  const float2* lp2 = reinterpret_cast<const float2*>(lp) + off;
+  if (blockIdx.y == 1) lattice_walk<true>(lp2, beta + off, costs + b, Tb, Ub, U1, u, sh0, sh1);
+  else lattice_walk<false>(lp2, alpha + off, costs + b, Tb, Ub, U1, u, sh0, sh1);
 }
 
 __global__ void coef_kernel(const float* __restrict__ lp, const float* __restrict__ lse,

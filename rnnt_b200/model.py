@@ -37,102 +37,27 @@ class RNNTModel(torch.nn.Module):
         Same per-utterance algorithm as rnnt/model.py:90-128 (blank or 10 emits advances the frame; stop at T_b or
         when len(tokens) incl. the seed blank reaches max_length), run for the whole batch at once with ALL loop state
         on the device: per step one joint+argmax kernel call for the batch, one incremental predictor update, and a
-        handful of elementwise ops -- captured once in a CUDA graph and replayed; the host only checks for completion
-        every `sync_every` steps (the reference syncs on `.item()` every step, model.py:113)."""
+        handful of elementwise ops -- captured once per shape in a CUDA graph and replayed; the host only checks for
+        completion every `sync_every` steps (the reference syncs on `.item()` every step, model.py:113)."""
         if not isinstance(self.predictor, ConvPredictor):
             raise ValueError("batched greedy decode supports ConvPredictor")
         if not audio_features.is_cuda:
             raise RuntimeError("rnnt_b200 decode runs on CUDA tensors only; there is no CPU fallback")
-        from .functional import joint_argmax_scratch
-        dev = audio_features.device
-        B, T, _ = audio_features.shape
-        V = self.joint.joint_ln.weight.shape[0]
-        blank = self.joint.blank_idx
-        audio_features = audio_features.contiguous()
-        lens = audio_feature_lens.to(dev, torch.int64).clamp(max=T)
         was_training = self.predictor.training
         self.predictor.eval()
         try:
-            stepper = ConvPredictorStepper(self.predictor, B, dev)
-            rows = torch.arange(B, device=dev)
-            t_idx = torch.zeros(B, dtype=torch.int64, device=dev)
-            per = torch.zeros(B, dtype=torch.int64, device=dev)
-            ntok = torch.ones(B, dtype=torch.int64, device=dev)          # counts the seed blank (model.py:53,64)
-            out = torch.full((B, max(max_length, 1)), blank, dtype=torch.int64, device=dev)
-            all_rows = torch.ones(B, dtype=torch.bool, device=dev)
-            feats = stepper.advance(torch.full((B,), blank, dtype=torch.int64, device=dev), all_rows).contiguous()
-            tok32 = torch.empty(B, dtype=torch.int32, device=dev)
-            margin = torch.empty(B, dtype=torch.float32, device=dev)
-            scratch = joint_argmax_scratch(B, V, dev)
-            max_steps = int(lens.max()) + max_length + 1
-            margin_log = torch.full((max_steps, B), float("inf"), device=dev) if return_margins else None
-            step_no = torch.zeros((), dtype=torch.int64, device=dev)
-            inf_row = torch.full((B,), float("inf"), device=dev)
-
-            def one_step():
-                active = (t_idx < lens) & (ntok < max_length)
-                a_rows = audio_features[rows, t_idx.clamp(max=T - 1)]
-                self.joint.argmax_step(a_rows, feats, return_margin=True, out=tok32, margin_out=margin,
-                                       scratch=scratch)
-                tok = tok32.to(torch.int64)
-                advance = active & ((tok == blank) | (per >= max_outputs_per_step))
-                emit = active & ~advance
-                if margin_log is not None:
-                    margin_log[step_no.clamp(max=max_steps - 1)] = torch.where(active, margin, inf_row)
-                    step_no.add_(1)
-                t_idx.add_(advance.to(torch.int64))
-                per.copy_(torch.where(advance, torch.zeros_like(per), per + emit.to(torch.int64)))
-                pos = ntok.clamp(max=out.shape[1]) - 1                      # token k (0-based, seed excluded) -> column k
-                cur = out[rows, pos.clamp(min=0)]
-                out[rows, pos.clamp(min=0)] = torch.where(emit, tok, cur)
-                ntok.add_(emit.to(torch.int64))
-                feats.copy_(torch.where(emit.view(-1, 1), stepper.advance(tok, emit), feats))
-
-            graph = None
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                if use_cuda_graph:
-                    try:
-                        saved = [x.clone() for x in (t_idx, per, ntok, out, feats, stepper.xs, stepper.ys, step_no)]
-                        side = torch.cuda.Stream(device=dev)
-                        side.wait_stream(torch.cuda.current_stream(dev))
-                        with torch.cuda.stream(side):
-                            one_step()                                  # warm-up outside capture
-                        torch.cuda.current_stream(dev).wait_stream(side)
-                        for x, sv in zip((t_idx, per, ntok, out, feats, stepper.xs, stepper.ys, step_no), saved):
-                            x.copy_(sv)
-                        if margin_log is not None:
-                            margin_log.fill_(float("inf"))
-                        graph = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(graph):
-                            one_step()
-                        for x, sv in zip((t_idx, per, ntok, out, feats, stepper.xs, stepper.ys, step_no), saved):
-                            x.copy_(sv)
-                        if margin_log is not None:
-                            margin_log.fill_(float("inf"))
-                    except Exception:
-                        graph = None
-                        for x, sv in zip((t_idx, per, ntok, out, feats, stepper.xs, stepper.ys, step_no), saved):
-                            x.copy_(sv)
-                done_steps = 0
-                while done_steps < max_steps:
-                    for _ in range(min(sync_every, max_steps - done_steps)):
-                        if graph is not None:
-                            graph.replay()
-                        else:
-                            one_step()
-                        done_steps += 1
-                    if not bool(((t_idx < lens) & (ntok < max_length)).any()):
-                        break
+            key = (tuple(audio_features.shape), str(audio_features.device), int(max_length), int(max_outputs_per_step),
+                   bool(return_margins), bool(use_cuda_graph))
+            sessions = self.__dict__.setdefault("_decode_sessions", {})
+            sess = sessions.get(key)
+            if sess is None:
+                if len(sessions) >= 4:
+                    sessions.clear()
+                sess = sessions[key] = _DecodeSession(self, audio_features, max_length, max_outputs_per_step,
+                                                      return_margins, use_cuda_graph)
+            return sess.run(audio_features, audio_feature_lens, sync_every)
         finally:
             self.predictor.train(was_training)
-        n = (ntok - 1).tolist()
-        out_host = out.tolist()
-        result = [out_host[b][: n[b]] for b in range(B)]
-        if return_margins:
-            ml = margin_log[:done_steps].t().tolist()
-            margins = [[m for m in ml[b] if m != float("inf")] for b in range(B)]
-            return result, margins
-        return result
 
     @torch.no_grad()
     def _greedy_decode_features_hostloop(self, audio_features, audio_feature_lens, max_length: int = 200,
@@ -184,6 +109,108 @@ class RNNTModel(torch.nn.Module):
         # the reference loops to audio_features.shape[1] (model.py:56,100), not to the computed length
         lens = torch.tensor([audio_features.shape[1]])
         return self.greedy_decode_features(audio_features, lens, max_length)[0]
+
+
+class _DecodeSession:
+    """Device-resident state of one batched greedy decode (shape-specific) plus the CUDA graph of one step."""
+
+    def __init__(self, model, audio_features, max_length, max_per_step, want_margins, use_graph):
+        from .functional import joint_argmax_scratch
+        self.model = model
+        dev = audio_features.device
+        B, T, _ = audio_features.shape
+        self.B, self.T, self.dev = B, T, dev
+        self.max_length, self.max_per_step = max_length, max_per_step
+        self.blank = model.joint.blank_idx
+        V = model.joint.joint_ln.weight.shape[0]
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.audio = torch.empty_like(audio_features, memory_format=torch.contiguous_format)
+        self.lens = torch.zeros(B, **i64)
+        self.rows = torch.arange(B, device=dev)
+        self.t_idx = torch.zeros(B, **i64)
+        self.per = torch.zeros(B, **i64)
+        self.ntok = torch.ones(B, **i64)                               # counts the seed blank (model.py:53,64)
+        self.out = torch.full((B, max(max_length, 1)), self.blank, **i64)
+        self.stepper = ConvPredictorStepper(model.predictor, B, dev)
+        self.feats = torch.zeros(B, model.joint.joint_ln.weight.shape[1], device=dev)
+        self.tok32 = torch.empty(B, dtype=torch.int32, device=dev)
+        self.margin = torch.empty(B, dtype=torch.float32, device=dev)
+        self.scratch = joint_argmax_scratch(B, V, dev)
+        self.max_steps = T + max_length + 1
+        self.margin_log = torch.full((self.max_steps, B), float("inf"), device=dev) if want_margins else None
+        self.step_no = torch.zeros((), **i64)
+        self.inf_row = torch.full((B,), float("inf"), device=dev)
+        self.all_rows = torch.ones(B, dtype=torch.bool, device=dev)
+        self.seed = torch.full((B,), self.blank, **i64)
+        self.use_graph = use_graph
+        self.graph = None
+
+    def _reset(self, audio_features, lens):
+        self.audio.copy_(audio_features)
+        self.lens.copy_(lens.to(self.dev, torch.int64).clamp(max=self.T))
+        self.t_idx.zero_(); self.per.zero_(); self.ntok.fill_(1); self.out.fill_(self.blank); self.step_no.zero_()
+        if self.margin_log is not None:
+            self.margin_log.fill_(float("inf"))
+        self.stepper.refresh()
+        self.feats.copy_(self.stepper.advance(self.seed, self.all_rows))     # predictor([blank]) (model.py:97-106)
+
+    def _one_step(self):
+        m, T = self.model, self.T
+        active = (self.t_idx < self.lens) & (self.ntok < self.max_length)
+        a_rows = self.audio[self.rows, self.t_idx.clamp(max=T - 1)]
+        m.joint.argmax_step(a_rows, self.feats, return_margin=True, out=self.tok32, margin_out=self.margin,
+                            scratch=self.scratch)
+        tok = self.tok32.to(torch.int64)
+        advance = active & ((tok == self.blank) | (self.per >= self.max_per_step))
+        emit = active & ~advance
+        if self.margin_log is not None:
+            self.margin_log[self.step_no.clamp(max=self.max_steps - 1)] = torch.where(active, self.margin, self.inf_row)
+            self.step_no.add_(1)
+        self.t_idx.add_(advance.to(torch.int64))
+        self.per.copy_(torch.where(advance, torch.zeros_like(self.per), self.per + emit.to(torch.int64)))
+        pos = (self.ntok.clamp(max=self.out.shape[1]) - 1).clamp(min=0)      # k-th emitted token -> column k
+        self.out[self.rows, pos] = torch.where(emit, tok, self.out[self.rows, pos])
+        self.ntok.add_(emit.to(torch.int64))
+        self.feats.copy_(torch.where(emit.view(-1, 1), self.stepper.advance(tok, emit), self.feats))
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._one_step()                                           # warm-up outside capture
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._one_step()
+        self.graph = graph
+
+    def run(self, audio_features, lens, sync_every):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            if self.use_graph and self.graph is None:
+                self._reset(audio_features, lens)
+                try:
+                    self._capture()
+                except Exception:
+                    self.graph, self.use_graph = None, False
+            self._reset(audio_features, lens)
+            limit = int(self.lens.max()) + self.max_length + 1
+            done = 0
+            while done < limit:
+                for _ in range(min(sync_every, limit - done)):
+                    if self.graph is not None:
+                        self.graph.replay()
+                    else:
+                        self._one_step()
+                    done += 1
+                if not bool(((self.t_idx < self.lens) & (self.ntok < self.max_length)).any()):
+                    break
+        n = (self.ntok - 1).tolist()
+        out_host = self.out.tolist()
+        result = [out_host[b][: n[b]] for b in range(self.B)]
+        if self.margin_log is not None:
+            ml = self.margin_log[:done].t().tolist()
+            return result, [[x for x in ml[b] if x != float("inf")] for b in range(self.B)]
+        return result
 
 
 def enable_zero_edit_mode(joint: JointNetwork, enabled: bool = True) -> None:

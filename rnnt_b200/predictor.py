@@ -72,13 +72,24 @@ class ConvPredictorStepper:
         p = predictor
         E = p.embedding.embedding_dim
         self.p = p
-        # conv weight (Co, Ci, k) -> (Co, k*Ci) matching the [oldest ... newest] concatenation of the taps
-        self.w1 = p.conv1.conv.weight.detach().permute(0, 2, 1).reshape(E, -1).contiguous()
-        self.w2 = p.conv2.conv.weight.detach().permute(0, 2, 1).reshape(E, -1).contiguous()
+        self.E = E
+        self.w1 = torch.empty(E, 3 * E, device=device)
+        self.w2 = torch.empty(E, 5 * E, device=device)
         self.b1 = p.conv1.conv.bias.detach()
         self.b2 = p.conv2.conv.bias.detach()
         self.xs = torch.zeros(batch, 2, E, device=device)
         self.ys = torch.zeros(batch, 4, E, device=device)
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        """Re-read the conv weights (in place, so captured CUDA graphs stay valid) and zero the streaming state."""
+        p, E = self.p, self.E
+        # conv weight (Co, Ci, k) -> (Co, k*Ci) matching the [oldest ... newest] concatenation of the taps
+        self.w1.copy_(p.conv1.conv.weight.detach().permute(0, 2, 1).reshape(E, -1))
+        self.w2.copy_(p.conv2.conv.weight.detach().permute(0, 2, 1).reshape(E, -1))
+        self.xs.zero_()
+        self.ys.zero_()
 
     @torch.no_grad()
     def advance(self, tokens, emit):

@@ -65,11 +65,13 @@ def decode():
     lens = torch.randint(T // 2, T + 1, (B,))
     lens[0] = T
     out = model.greedy_decode_features(feats, lens, max_length=200)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     out, margins = model.greedy_decode_features(feats, lens, max_length=200, return_margins=True)
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out2 = model.greedy_decode_features(feats, lens, max_length=200)
+    torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    assert out2 == out
     steps = max(len(m) for m in margins)
     t1 = time.perf_counter()
     out_h = model._greedy_decode_features_hostloop(feats, lens, max_length=200)
