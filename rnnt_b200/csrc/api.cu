@@ -41,9 +41,11 @@ WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles) {
   return w;
 }
 
-int check_common(const void* enc, int64_t enc_sb, int64_t enc_st, const void* pred, int B, int T, int U1, int H,
+int check_common(const void* enc, int64_t& enc_sb, int64_t& enc_st, const void* pred, int B, int T, int U1, int H,
                  int V, int* blank) {
   RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && H > 0 && V > 1, -1, "invalid shape B=%d T=%d U1=%d H=%d V=%d", B, T, U1, H, V);
+  if (T == 1) enc_st = H;                      // strides of size-1 dimensions carry no information
+  if (B == 1) enc_sb = static_cast<int64_t>(T) * enc_st;
   RB_REQUIRE(H % 8 == 0, -2, "hidden_features must be a multiple of 8 (got %d)", H);
   RB_REQUIRE(U1 <= 1024, -5, "U+1 must be <= 1024 (got %d)", U1);
   RB_REQUIRE((reinterpret_cast<uintptr_t>(enc) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred) & 15) == 0, -3,
