@@ -324,6 +324,12 @@ def run_gpu_arm(args):
                 frac = 1.0 if nm == "joint_gemm_fwd" else bwd_frac
                 kern[nm]["flops_per_step"] = gemm_flops_per_step_rank * frac
                 kern[nm]["tflops"] = gemm_flops_per_step_rank * frac / (per_step_ms * 1e-3) / 1e12
+            if nm == "lattice":
+                # algorithmic bytes: each direction reads lp (8 B/cell) and writes alpha or beta (4 B/cell)
+                lat_bytes = B * T * (U + 1) * 24
+                kern[nm]["gbs"] = lat_bytes / (per_step_ms * 1e-3) / 1e9
+                kern[nm]["hbm_frac"] = kern[nm]["gbs"] / peaks["hbm"]
+                kern[nm]["ns_per_antidiagonal"] = per_step_ms * 1e6 / (T + U)
         gemms = {k: v for k, v in kern.items() if "tflops" in v}
         if not gemms:   # --no-kernel-profile: no per-kernel events were recorded
             gemms = {"whole_step": dict(ms_per_step=ms_step, launches_per_step=1.0,
