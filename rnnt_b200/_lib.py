@@ -43,9 +43,15 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"rnnt_b200: CUDA extension not built ({LIB_PATH} missing). Run `python -m rnnt_b200.build` "
-                "(needs nvcc); there is no CPU or PyTorch fallback for this path.")
+            # first use in a fresh checkout: compile in-tree if a CUDA toolchain is present, otherwise fail loudly
+            try:
+                from .build import build_extension
+                build_extension()
+            except Exception as exc:
+                raise RuntimeError(
+                    f"rnnt_b200: CUDA extension not built ({LIB_PATH} missing) and building it failed: {exc}. "
+                    "Run `python -m rnnt_b200.build` (needs nvcc); there is no CPU or PyTorch fallback for this "
+                    "path.") from exc
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)   # AttributeError if the symbol is not exported
