@@ -87,6 +87,23 @@ int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const floa
                            const float* W, const float* bias, int N, int H, int V, int32_t* tokens, float* margin,
                            void* scratch, void* stream);
 
+/* Whole batched greedy decode in one persistent cooperative kernel (fp32).  Replaces the host loop of
+ * rnnt/model.py:90-128 (_greedy_decode_conv) including the ConvPredictor re-run (rnnt/predictor.py:209-229), evaluated
+ * incrementally (the predictor is causal with a 7-token receptive field).  enc (B,T,H) are the encoder features,
+ * T_len (B) their lengths; conv1_w / conv2_w are the Conv1d weights re-laid as (E, 3E) / (E, 5E) with taps ordered
+ * oldest..newest (weight.permute(0,2,1).reshape(E,-1)); every other parameter is the module's tensor as is.
+ * tokens (B, max_len) int32 receives the emitted tokens, n_tokens (B) = 1 + their count (the seed blank is counted,
+ * as rnnt/model.py:53,64 does).  margins_out (optional, (T+max_len+2, B) fp32, caller-initialised) receives the top-2
+ * logit gap at [step, b] for every step utterance b was active in.  scratch: rnnt_b200_greedy_decode_scratch_bytes. */
+size_t rnnt_b200_greedy_decode_scratch_bytes(int B, int H, int V, int E);
+int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, const int32_t* T_len,
+                            const float* joint_w, const float* joint_b, const float* emb, const float* ln1_w,
+                            const float* ln1_b, const float* conv1_w, const float* conv1_b, const float* conv2_w,
+                            const float* conv2_b, const float* lin_w, const float* lin_b, const float* ln2_w,
+                            const float* ln2_b, int B, int T, int H, int V, int E, int blank, int max_len,
+                            int max_per_frame, int32_t* tokens, int32_t* n_tokens, float* margins_out, void* scratch,
+                            void* stream);
+
 /* Opt-in measurement hook (bench.py): between begin and end every kernel launch of the library is bracketed by
  * CUDA events on its launch stream.  end() synchronises on those events and returns, per kernel family, the summed
  * device time in ms and the number of launches.  HOST pointers.  Families: 0 prep (tile table, weight conversion,

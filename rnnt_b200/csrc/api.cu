@@ -269,6 +269,32 @@ int rnnt_b200_loss_dense_bwd(const float* logits, const int32_t* targets, const 
   return rb::launch_dense_grads(logits, targets, U1 - 1, T_len, U_len, coef, B, T, U1, V, blank, clamp, grads, stream);
 }
 
+size_t rnnt_b200_greedy_decode_scratch_bytes(int B, int H, int V, int E) {
+  return rb::greedy_decode_scratch_bytes(B, H, V, E);
+}
+
+int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, const int32_t* T_len,
+                            const float* joint_w, const float* joint_b, const float* emb, const float* ln1_w,
+                            const float* ln1_b, const float* conv1_w, const float* conv1_b, const float* conv2_w,
+                            const float* conv2_b, const float* lin_w, const float* lin_b, const float* ln2_w,
+                            const float* ln2_b, int B, int T, int H, int V, int E, int blank, int max_len,
+                            int max_per_frame, int32_t* tokens, int32_t* n_tokens, float* margins_out, void* scratch,
+                            void* stream) {
+  RB_REQUIRE(B > 0 && T > 0 && H > 0 && V > 1 && E > 0 && max_len >= 1 && max_per_frame >= 0, -1, "invalid shape");
+  RB_REQUIRE(blank >= 0 && blank < V, -4, "blank index out of range");
+  RB_REQUIRE(H % 4 == 0 && E % 4 == 0 && enc_st % 4 == 0 && enc_sb % 4 == 0, -2,
+             "decode kernel needs hidden / embedding sizes and strides that are multiples of 4");
+  rb::DecodeArgs a{};
+  a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st; a.T_len = T_len;
+  a.Wj = joint_w; a.bj = joint_b; a.emb = emb; a.ln1_w = ln1_w; a.ln1_b = ln1_b;
+  a.w1 = conv1_w; a.b1 = conv1_b; a.w2 = conv2_w; a.b2 = conv2_b; a.wl = lin_w; a.bl = lin_b;
+  a.ln2_w = ln2_w; a.ln2_b = ln2_b;
+  a.B = B; a.T = T; a.H = H; a.V = V; a.E = E; a.blank = blank; a.max_len = max_len;
+  a.max_per_frame = max_per_frame; a.max_steps = T + max_len + 1;
+  a.tokens = tokens; a.ntok = n_tokens; a.margins = margins_out;
+  return rb::launch_greedy_decode(a, static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));
+}
+
 int rnnt_b200_profile_begin(void) { return rb::prof_begin(); }
 int rnnt_b200_profile_end(float* ms, int64_t* launches) {
   long long l[rb::kProfFamilies];

@@ -63,6 +63,28 @@ struct DwArgs {
   int ksplit;
 };
 
+struct DecodeArgs {
+  const float* enc;        // (B,T,H) fp32, H contiguous
+  long long enc_sb, enc_st;
+  const int* T_len;        // (B) frames per utterance
+  const float* Wj; const float* bj;                       // joint_ln (V,H), (V)
+  const float* emb; const float* ln1_w; const float* ln1_b;   // embedding (NS,E), input LayerNorm (E)
+  const float* w1; const float* b1;                       // conv1 as (E, 3E): taps oldest..newest
+  const float* w2; const float* b2;                       // conv2 as (E, 5E)
+  const float* wl; const float* bl;                       // linear (H,E), (H)
+  const float* ln2_w; const float* ln2_b;                 // output LayerNorm (H)
+  int B, T, H, V, E, blank, max_len, max_per_frame, max_steps, smem_floats;
+  int* tokens;             // (B, max_len) emitted tokens (seed blank excluded)
+  int* ntok;               // (B) 1 + number of emitted tokens
+  // scratch (carved by the launcher)
+  float *feats, *hbuf, *logits, *xs, *ys, *xnew, *ynew, *z, *lin, *margins;
+  int *t_idx, *per, *emit, *rows, *flags;
+  long long* prof;         // 8 cycle counters (block 0): P1, P2, P3, P4, P5, P6, -, grid barriers
+};
+
+size_t greedy_decode_scratch_bytes(int B, int H, int V, int E);
+int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream);
+
 size_t joint_gemm_smem_bytes();
 int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
                       const JointArgs& args, int grid, cudaStream_t stream);

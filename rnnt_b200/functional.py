@@ -20,6 +20,7 @@ _DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(1 << 30)))
 # (active lattice tiles, total lattice tiles) here.  Off by default (costs two tiny copies per step).
 COLLECT_BACKWARD_STATS = False
 _last_backward_stats = None
+_last_decode_phase_cycles = None   # int64[8] cycle counters of the last decode kernel (P1..P6, -, grid barriers)
 
 
 def last_backward_stats():
@@ -303,3 +304,50 @@ def joint_argmax(audio_rows, text_rows, weight, bias, return_margin: bool = Fals
             weight.data_ptr(), bias.data_ptr(), N, H, V, tokens.data_ptr(),
             margin.data_ptr() if return_margin else None, scratch.data_ptr(), _stream_ptr(dev)), "joint_argmax")
     return (tokens, margin) if return_margin else tokens
+
+
+def greedy_decode(audio_features, audio_feature_lens, joint_weight, joint_bias, predictor, blank: int,
+                  max_length: int = 200, max_outputs_per_step: int = 10, return_margins: bool = False):
+    """Batched greedy decode (rnnt/model.py:90-128 for every utterance of a batch) in ONE persistent CUDA kernel.
+
+    audio_features (B,T,H) fp32, audio_feature_lens (B); `predictor` is a ConvPredictor-shaped module (embedding,
+    input_layer_norm, conv1.conv, conv2.conv, linear, output_layer_norm).  Returns list[list[int]] (and, optionally,
+    per-utterance lists of top-2 logit margins for every step the utterance was active in)."""
+    _require_cuda(audio_features, joint_weight, joint_bias)
+    L = _lib.lib()
+    dev = audio_features.device
+    B, T, H = audio_features.shape
+    V = joint_weight.shape[0]
+    p = predictor
+    E = p.embedding.embedding_dim
+    if p.linear.out_features != H or joint_weight.shape[1] != H:
+        raise RuntimeError("predictor output, encoder features and joint hidden size must agree")
+    if p.conv1.conv.kernel_size[0] != 3 or p.conv2.conv.kernel_size[0] != 5:
+        raise RuntimeError("decode kernel expects ConvPredictor's kernel sizes 3 and 5")
+    f = lambda t: t.detach().to(dev, torch.float32).contiguous()
+    enc = f(audio_features)
+    w1 = f(p.conv1.conv.weight.detach().permute(0, 2, 1).reshape(E, -1))
+    w2 = f(p.conv2.conv.weight.detach().permute(0, 2, 1).reshape(E, -1))
+    params = [f(joint_weight), f(joint_bias), f(p.embedding.weight), f(p.input_layer_norm.weight),
+              f(p.input_layer_norm.bias), w1, f(p.conv1.conv.bias), w2, f(p.conv2.conv.bias), f(p.linear.weight),
+              f(p.linear.bias), f(p.output_layer_norm.weight), f(p.output_layer_norm.bias)]
+    lens = audio_feature_lens.to(dev, torch.int32).clamp(max=T).contiguous()
+    max_len = max(int(max_length), 1)
+    tokens = torch.zeros(B, max_len, dtype=torch.int32, device=dev)
+    ntok = torch.ones(B, dtype=torch.int32, device=dev)
+    margins = torch.full((T + max_len + 2, B), float("inf"), device=dev) if return_margins else None
+    scratch = torch.empty(L.rnnt_b200_greedy_decode_scratch_bytes(B, H, V, E), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.rnnt_b200_greedy_decode(
+            enc.data_ptr(), enc.stride(0), enc.stride(1), lens.data_ptr(), *[t.data_ptr() for t in params],
+            B, T, H, V, E, int(blank), max_len, int(max_outputs_per_step), tokens.data_ptr(), ntok.data_ptr(),
+            margins.data_ptr() if return_margins else None, scratch.data_ptr(), _stream_ptr(dev)), "greedy_decode")
+    global _last_decode_phase_cycles
+    _last_decode_phase_cycles = scratch[-64:].view(torch.int64)
+    n = (ntok - 1).tolist()
+    toks = tokens.tolist()
+    result = [toks[b][: n[b]] for b in range(B)]
+    if return_margins:
+        ml = margins.t().tolist()
+        return result, [[x for x in ml[b] if x != float("inf")] for b in range(B)]
+    return result

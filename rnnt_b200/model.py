@@ -31,18 +31,26 @@ class RNNTModel(torch.nn.Module):
     @torch.no_grad()
     def greedy_decode_features(self, audio_features, audio_feature_lens, max_length: int = 200,
                                max_outputs_per_step: int = 10, return_margins: bool = False,
-                               use_cuda_graph: bool = True, sync_every: int = 16):
+                               use_cuda_graph: bool = True, sync_every: int = 16, engine: str = "kernel"):
         """Batched greedy decode on given encoder features (B,T,H) with per-utterance lengths.
 
         Same per-utterance algorithm as rnnt/model.py:90-128 (blank or 10 emits advances the frame; stop at T_b or
         when len(tokens) incl. the seed blank reaches max_length), run for the whole batch at once with ALL loop state
         on the device: per step one joint+argmax kernel call for the batch, one incremental predictor update, and a
-        handful of elementwise ops -- captured once per shape in a CUDA graph and replayed; the host only checks for
-        completion every `sync_every` steps (the reference syncs on `.item()` every step, model.py:113)."""
+        handful of elementwise ops.  engine="kernel" (default) runs everything inside ONE persistent cooperative CUDA
+        kernel (`rnnt_b200_greedy_decode`); engine="graph" replays a captured CUDA graph of torch ops + the argmax
+        kernel per step and checks for completion every `sync_every` steps (kept as an independent cross-check and
+        for joints with audio_ln / text_ln).  The reference syncs on `.item()` every step (model.py:113)."""
         if not isinstance(self.predictor, ConvPredictor):
             raise ValueError("batched greedy decode supports ConvPredictor")
         if not audio_features.is_cuda:
             raise RuntimeError("rnnt_b200 decode runs on CUDA tensors only; there is no CPU fallback")
+        if engine == "kernel" and not hasattr(self.joint, "audio_ln") and not hasattr(self.joint, "text_ln"):
+            # the whole loop (joint step, argmax, per-utterance state, incremental predictor) in one persistent kernel
+            from .functional import greedy_decode
+            return greedy_decode(audio_features, audio_feature_lens, self.joint.joint_ln.weight,
+                                 self.joint.joint_ln.bias, self.predictor, self.joint.blank_idx, max_length,
+                                 max_outputs_per_step, return_margins)
         was_training = self.predictor.training
         self.predictor.eval()
         try:

@@ -72,16 +72,23 @@ def decode():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     assert out2 == out
+    cyc = RF._last_decode_phase_cycles.tolist()
+    print('  decode kernel phase cycles (block 0): P1 %d P2 %d P3 %d P4 %d P5 %d P6 %d barriers %d' % (cyc[0], cyc[1], cyc[2], cyc[3], cyc[4], cyc[5], cyc[7]), ' total us @1.9GHz: %.0f' % (sum(cyc)/1900))
     steps = max(len(m) for m in margins)
     t1 = time.perf_counter()
     out_h = model._greedy_decode_features_hostloop(feats, lens, max_length=200)
     torch.cuda.synchronize()
     print(f"  host-driven loop: {(time.perf_counter()-t1)*1e3:.1f} ms, identical tokens: {out_h == out}")
     t1 = time.perf_counter()
-    out_e = model.greedy_decode_features(feats, lens, max_length=200, use_cuda_graph=False)
+    out_e = model.greedy_decode_features(feats, lens, max_length=200, use_cuda_graph=False, engine="graph")
     torch.cuda.synchronize()
     print(f"  eager device loop: {(time.perf_counter()-t1)*1e3:.1f} ms, identical tokens: {out_e == out}")
-    print(f"decode B{B} T{T}: {dt*1e3:.1f} ms total, {steps} batched steps ({dt/steps*1e6:.0f} us/step), "
+    model.greedy_decode_features(feats, lens, max_length=200, engine="graph")
+    t1 = time.perf_counter()
+    out_g = model.greedy_decode_features(feats, lens, max_length=200, engine="graph")
+    torch.cuda.synchronize()
+    print(f"  CUDA-graph device loop: {(time.perf_counter()-t1)*1e3:.1f} ms, identical tokens: {out_g == out}")
+    print(f"decode (persistent kernel) B{B} T{T}: {dt*1e3:.1f} ms total, {steps} batched steps ({dt/steps*1e6:.0f} us/step), "
           f"tokens/utt mean {sum(len(o) for o in out)/B:.1f}, frames/s {int(lens.sum())/dt:.0f}, min top-2 margin {min(min(m) for m in margins):.2e}")
     # reference algorithm, utterance by utterance (rnnt/model.py:90-128 restated with torch ops on the GPU, fp32)
     mism = 0

@@ -277,9 +277,10 @@ def test_greedy_decode_matches_reference_golden(golden_dir):
         want = g["tok_flat"][off:off + n].tolist()
         off += n
         assert got[i] == want, (i, min(margins[i]))
-    # the eager (no CUDA graph) device loop and the host-driven loop agree with it
-    assert model.greedy_decode_features(feats, torch.from_numpy(g["T_len"]), max_length=int(g["max_length"]),
-                                        use_cuda_graph=False) == got
+    # the torch-op device loop (CUDA graph replay and eager) and the host-driven loop agree with the persistent kernel
+    for graph in (True, False):
+        assert model.greedy_decode_features(feats, torch.from_numpy(g["T_len"]), max_length=int(g["max_length"]),
+                                            use_cuda_graph=graph, engine="graph") == got
     assert model._greedy_decode_features_hostloop(feats, torch.from_numpy(g["T_len"]),
                                                   max_length=int(g["max_length"])) == got
     # reference-signature entry: batch of one through an (identity) encoder, list[int] out
