@@ -160,6 +160,73 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------- other configs
+def other_configs(torch, dev):
+    """Short single-GPU runs of the remaining BASELINE.json configs (parity for these lives in tests/; this only
+    reports their throughput next to the headline line)."""
+    import rnnt_b200
+    from rnnt_b200.functional import joint_rnnt_loss
+
+    def timed(fn, n):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def loss_cfg(b, t, u, v, ragged, n):
+        g = torch.Generator().manual_seed(77)
+        enc = torch.randn(b, t, H, generator=g).to(dev).requires_grad_(True)
+        pred = torch.randn(b, u + 1, H, generator=g).to(dev).requires_grad_(True)
+        bound = 1.0 / (H ** 0.5)
+        W = ((torch.rand(v, H, generator=g) * 2 - 1) * bound).to(dev).requires_grad_(True)
+        bias = ((torch.rand(v, generator=g) * 2 - 1) * bound).to(dev).requires_grad_(True)
+        tg = torch.randint(0, v - 1, (b, u), generator=g, dtype=torch.int32).to(dev)
+        if ragged:
+            tl = torch.randint(t // 2, t + 1, (b,), generator=g, dtype=torch.int32); tl[0] = t
+            ul = torch.randint(u // 2, u + 1, (b,), generator=g, dtype=torch.int32); ul[-1] = u
+        else:
+            tl = torch.full((b,), t, dtype=torch.int32); ul = torch.full((b,), u, dtype=torch.int32)
+        cells = int((tl.long() * (ul.long() + 1)).sum())
+        tl, ul = tl.to(dev), ul.to(dev)
+
+        def fn():
+            for x in (enc, pred, W, bias):
+                x.grad = None
+            joint_rnnt_loss(enc, pred, W, bias, tg, tl, ul, validate=False).backward()
+        torch.cuda.reset_peak_memory_stats(dev)
+        ms = timed(fn, n)
+        return dict(ms_per_step=ms, valid_cells=cells, value=cells / (ms * 1e-3), unit=UNIT,
+                    peak_mem_gib=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+
+    out = {}
+    out["cpu_reference_shape_B4_T200_U40_V1024"] = loss_cfg(4, 200, 40, 1024, False, 20)
+    out["ragged_B32_T400_U100_V1024"] = loss_cfg(32, 400, 100, 1024, True, 5)
+    out["stress_B8_T1500_U300_V4096_ragged"] = loss_cfg(8, 1500, 300, 4096, True, 2)
+    # batched greedy decode, B=64, T=400, ConvPredictor at default init, max_length 200
+    torch.manual_seed(0)
+    joint = rnnt_b200.JointNetwork(-1, -1, H, V)
+    with torch.no_grad():
+        joint.joint_ln.bias[V - 1] += 1.0
+    model = rnnt_b200.RNNTModel(rnnt_b200.ConvPredictor(V, H, 512, 0.3), torch.nn.Identity(), joint).to(dev).eval()
+    feats = torch.randn(64, 400, H, device=dev)
+    lens = torch.randint(200, 401, (64,)); lens[0] = 400
+    model.greedy_decode_features(feats, lens, max_length=200)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    toks = model.greedy_decode_features(feats, lens, max_length=200)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["greedy_decode_B64_T400"] = dict(ms_total=dt * 1e3, frames=int(lens.sum()), frames_per_s=int(lens.sum()) / dt,
+                                         tokens=sum(len(x) for x in toks),
+                                         note="whole loop in one persistent kernel, wall clock incl. result read-back")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
     import torch
@@ -349,6 +416,12 @@ def run_gpu_arm(args):
                         whole_step_frac_credited=(value / world) * 3 * FLOP_PER_CELL_GEMM / (peaks["tflops"] * 1e12),
                         kernels=kern)
         cpu_base, _ = time_cpu_reference(1, 1) if world == 1 and not args.no_cpu_baseline else (None, None)
+        extra = None
+        if world == 1 and not args.no_extra:
+            try:
+                extra = other_configs(torch, dev)
+            except Exception as exc:      # the headline line must not depend on the side runs
+                extra = dict(error=repr(exc))
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp16",
                     data="synthetic",
@@ -372,6 +445,8 @@ def run_gpu_arm(args):
                     roofline=roofline)
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if extra is not None:
+            line["other_configs"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -385,6 +460,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true", help="skip the per-kernel CUDA events")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     ap.add_argument("--all-tiles", action="store_true",
                     help="backward processes every lattice tile (also those whose fp16 gradients are all zero)")
     args = ap.parse_args()
