@@ -50,8 +50,8 @@ int check_common(const void* enc, int64_t& enc_sb, int64_t& enc_st, const void* 
   RB_REQUIRE(U1 <= 1024, -5, "U+1 must be <= 1024 (got %d)", U1);
   RB_REQUIRE((reinterpret_cast<uintptr_t>(enc) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred) & 15) == 0, -3,
              "enc/pred must be 16-byte aligned");
-  RB_REQUIRE(enc_st % 2 == 0 && enc_sb % 2 == 0 && enc_st >= H, -3,
-             "audio features must be contiguous in the feature dimension with even strides");
+  RB_REQUIRE(enc_st % 4 == 0 && enc_sb % 4 == 0 && enc_st >= H, -3,
+             "audio features must be contiguous in the feature dimension with strides that are multiples of 4");
   if (*blank < 0) *blank += V;
   RB_REQUIRE(*blank >= 0 && *blank < V, -4, "blank index out of range");
   return 0;

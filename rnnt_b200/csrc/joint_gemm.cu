@@ -305,64 +305,71 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     if (MODE == 1 && set_tid == 0) tma_store_wait_all<0>();
   } else if (warp >= kFirstProdWarp && warp < kFirstProdWarp + kNumProdWarps) {
     // ===================================================================== A producers
-    const int rg = warp - kFirstProdWarp;  // rows rg*16 .. rg*16+15  <->  t-rows 2rg, 2rg+1, all 8 u
-    const int kp = lane;                   // column pair within the 64-wide K chunk
+    // Warp rg produces rows rg*16 .. rg*16+15 of the tile (t-rows 2rg, 2rg+1; all 8 u).  Lane l owns the 16-byte
+    // column chunk c = l & 7 (8 hidden units) of the four rows rs, rs+4, rs+8, rs+12 (rs = l >> 3), i.e. the pairs
+    // (t-row 0|1) x (u = rs | rs+4): 4 x 8 inputs, 32 tanh, four 16-byte shared stores.  Few wide stores matter:
+    // fence.proxy.async is a MEMBAR.ALL.CTA whose latency grows with the number of shared stores in flight.
+    const int rg = warp - kFirstProdWarp;
+    const int c = lane & 7, rs = lane >> 3;
     uint32_t it = 0;
     for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
       const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
       const float* e_ptr[2];
-      const float* p_ptr[8];
+      const float* p_ptr[2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + 2 * rg + i, p.T - 1)) * p.enc_st;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        p_ptr[j] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + j, p.U1 - 1)) * p.pred_su;
-
-      float2 e_cur[2], p_cur[8];
-      auto load_chunk = [&](int kc, float2 (&e)[2], float2 (&q)[8]) {
-        const int col = kc * kBK + 2 * kp;
+      for (int i = 0; i < 2; ++i) {
+        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + 2 * rg + i, p.T - 1)) * p.enc_st + 8 * c;
+        p_ptr[i] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + rs + 4 * i, p.U1 - 1)) * p.pred_su + 8 * c;
+      }
+      float4 e_cur[2][2], p_cur[2][2];
+      auto load_chunk = [&](int kc, float4 (&e)[2][2], float4 (&q)[2][2]) {
+        const int col = kc * kBK + 8 * c;
         if (col < p.H) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) e[i] = __ldg(reinterpret_cast<const float2*>(e_ptr[i] + col));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) q[j] = __ldg(reinterpret_cast<const float2*>(p_ptr[j] + col));
+          for (int i = 0; i < 2; ++i) {
+            e[i][0] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK));
+            e[i][1] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK) + 1);
+            q[i][0] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK));
+            q[i][1] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK) + 1);
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) e[i] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) q[j] = make_float2(0.f, 0.f);
+          for (int i = 0; i < 2; ++i) {
+            e[i][0] = e[i][1] = q[i][0] = q[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       };
       load_chunk(0, e_cur, p_cur);
       for (int pass = 0; pass < npass; ++pass) {
         for (int kc = 0; kc < nk; ++kc, ++it) {
-          float2 e_nxt[2], p_nxt[8];
-          const int kn = (kc + 1 < nk) ? kc + 1 : 0;
-          if (kc + 1 < nk || pass + 1 < npass) load_chunk(kn, e_nxt, p_nxt);
           const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
           mbar_wait(a_empty + 8 * s, ph ^ 1);
           const uint32_t stage = a_ring + s * kBytesA;
-          if (!(p.dbg & 2))
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 2; ++i) {        // t-row
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float h0 = tanh_approx(e_cur[i].x + p_cur[j].x);
-              const float h1 = tanh_approx(e_cur[i].y + p_cur[j].y);
-              const int r = rg * 16 + i * 8 + j;
-              const uint32_t addr = stage + r * 128 + ((((uint32_t)kp >> 2) ^ (uint32_t)j) << 4) + ((kp & 3) << 2);
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_f16x2(h0, h1)) : "memory");
+              for (int j = 0; j < 2; ++j) {      // u = rs + 4j
+                const float4 a0 = e_cur[i][0], a1 = e_cur[i][1], b0 = p_cur[j][0], b1 = p_cur[j][1];
+                const uint32_t w0 = pack_f16x2(tanh_approx(a0.x + b0.x), tanh_approx(a0.y + b0.y));
+                const uint32_t w1 = pack_f16x2(tanh_approx(a0.z + b0.z), tanh_approx(a0.w + b0.w));
+                const uint32_t w2 = pack_f16x2(tanh_approx(a1.x + b1.x), tanh_approx(a1.y + b1.y));
+                const uint32_t w3 = pack_f16x2(tanh_approx(a1.z + b1.z), tanh_approx(a1.w + b1.w));
+                const int ui = rs + 4 * j;                       // = row & 7
+                const int r = rg * 16 + i * 8 + ui;
+                const uint32_t addr = stage + r * 128 + ((static_cast<uint32_t>(c) ^ static_cast<uint32_t>(ui)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                             : "memory");
+              }
             }
           }
+          // the inputs of the next chunk are requested now (their registers are free again); the fence, the barrier
+          // hand-off and the other producer warp of this scheduler cover the load latency
+          if (kc + 1 < nk || pass + 1 < npass) load_chunk((kc + 1 < nk) ? kc + 1 : 0, e_cur, p_cur);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(a_full + 8 * s);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) e_cur[i] = e_nxt[i];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) p_cur[j] = p_nxt[j];
         }
       }
     }

@@ -90,7 +90,7 @@ class _FusedJointLoss(torch.autograd.Function):
         U1 = pred.shape[1]
         V = weight.shape[0]
         dev = enc.device
-        enc_c = enc if enc.stride(2) == 1 and enc.stride(1) % 2 == 0 and enc.stride(0) % 2 == 0 else enc.contiguous()
+        enc_c = enc if enc.stride(2) == 1 and enc.stride(1) % 4 == 0 and enc.stride(0) % 4 == 0 else enc.contiguous()
         pred_c = pred.contiguous()
         weight_c = weight.contiguous()
         bias_c = bias.contiguous()
