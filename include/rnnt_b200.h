@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RNNT_B200_ABI_VERSION 1
+#define RNNT_B200_ABI_VERSION 2
 
 int rnnt_b200_abi_version(void);
 const char* rnnt_b200_last_error(void);
@@ -35,34 +35,43 @@ const char* rnnt_b200_last_error(void);
 /* Upper bound on the number of 16(t) x 8(u) lattice tiles of a (B,T,U1) batch. */
 int64_t rnnt_b200_max_tiles(int B, int T, int U1);
 
-/* Workspace sizes in bytes.  ring_tiles = number of 128-cell tiles the backward's 16-bit gradient / activation
- * rings hold at once (fixed size, independent of B*T*U1); the backward walks the batch in chunks of that size. */
-int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, size_t* fwd_bytes,
-                              size_t* bwd_bytes);
+/* Size in bytes of the optional activation residual `hidden`: h = tanh(enc + pred) as fp16, one 128-row block per
+ * lattice tile, rows padded to a multiple of 64 hidden units.  The reference's autograd saves the same tensor in fp32
+ * (rnnt/joint.py:37).  With it the backward does not recompute the tanh; without it (NULL) it does. */
+size_t rnnt_b200_hidden_bytes(int B, int T, int U1, int H);
+
+/* Workspace sizes in bytes.  ring_tiles = number of 128-cell tiles the backward's 16-bit gradient (and, without a
+ * hidden residual, activation) ring holds at once (fixed size, independent of B*T*U1); the backward walks the batch in
+ * chunks of that size.  have_hidden = 1 if `hidden` will be passed to the calls (smaller workspaces). */
+int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
+                              size_t* fwd_bytes, size_t* bwd_bytes);
 
 /* Fused joint + loss forward.  Replaces rnnt/joint.py:25-39 followed by rnnt/model.py:35-41 (reduction="none").
  *   enc  (B,T,H) fp32 with element strides (enc_sb, enc_st, 1)      pred (B,U1,H) fp32 contiguous
  *   W    (V,H) fp32 (joint_ln.weight)                                bias (V) fp32 (joint_ln.bias)
  * Outputs (all fully written for valid cells): costs (B), lp (B,T,U1,2) = log p(blank), log p(label),
  * lse (B,T,U1), alpha (B,T,U1), beta (B,T,U1).  These five are the residuals the backward consumes.
+ * hidden (optional, rnnt_b200_hidden_bytes, 128-byte aligned): receives the fp16 activations for the backward; NULL
+ * keeps them in a small per-SM scratch inside the workspace (loss-only evaluation, or a recomputing backward).
  * status (optional, may be NULL): device int set to 1 if any length is out of range. */
 int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, float* costs, float* lp, float* lse,
-                             float* alpha, float* beta, int32_t* status, void* workspace, size_t workspace_bytes,
-                             void* stream);
+                             float* alpha, float* beta, void* hidden, int32_t* status, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* Fused backward.  Replaces RnntLoss.backward + autograd through rnnt/joint.py:32-39.
  * dcost (B) = d loss / d cost_b (1/B for reduction="mean"); clamp <= 0 disables gradient clamping.
+ * hidden = the buffer the forward filled, or NULL to recompute the activations (memory-lean mode).
  * Outputs are overwritten: d_enc (B,T,H) contiguous, d_pred (B,U1,H), dW (V,H), dbias (V), all fp32.
  * Lattice tiles whose scaled logit-gradients are all below fp16 resolution (occupancy < 2^-25 of max|dcost|) are
  * exactly zero in the gradient ring and are skipped; flags bit 0 = 1 disables the skipping (every tile is processed). */
 int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
-                             const float* alpha, const float* beta, const float* dcost, float clamp, float* d_enc,
-                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, int flags,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             const float* alpha, const float* beta, const void* hidden, const float* dcost,
+                             float clamp, float* d_enc, float* d_pred, float* dW, float* dbias, int64_t ring_tiles,
+                             int flags, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss on already materialised logits (B,T,U1,V) fp32 contiguous -- the literal torchaudio.functional.rnnt_loss
  * call of rnnt/model.py:35-41 for callers that hold logits (e.g. eval.py:76 style uses).  fwd writes costs and the
@@ -115,12 +124,13 @@ int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
 /* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
  *   offsets[0] tile table: B+1 int32 prefix sums of tiles per utterance, status, {S, 1/S} (fp32), n_active tiles
  *   offsets[1] W as fp16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
- *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] bf16
- *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16     offsets[6] total bytes
+ *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] fp16
+ *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16 (-1 with have_hidden)
+ *   offsets[6] bytes that satisfy both the forward and the backward call
  *   offsets[7] work list of active lattice tiles (int32).
  * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
-int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int64_t* offsets /*[8]*/,
-                              int* Hp, int* Vp);
+int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
+                              int64_t* offsets /*[8]*/, int* Hp, int* Vp);
 
 #ifdef __cplusplus
 }

@@ -17,11 +17,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t tile_off, wb, bias2, coef, flags, tile_list, g_ring, h_ring, total_fwd, total_bwd;
-  int Hp, Vp;
+  size_t tile_off, wb, bias2, h_scratch, coef, flags, tile_list, g_ring, h_ring, total_fwd, total_bwd;
+  int Hp, Vp, scratch_tiles;
 };
 
-WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles) {
+// have_hidden: the caller supplies the activation residual buffer (rnnt_b200_hidden_bytes).  Then the forward needs
+// no per-CTA activation scratch and the backward ring holds the logit-gradients only.
+WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, bool have_hidden) {
   WsLayout w;
   w.Hp = round_up(H, 64);
   w.Vp = round_up(V, 256);
@@ -29,14 +31,18 @@ WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles) {
   w.tile_off = off; off = align_up(off + (static_cast<size_t>(B) + 6) * sizeof(int), 1024);   // + status, {S, 1/S}, n_active
   w.wb = off;       off = align_up(off + static_cast<size_t>(w.Vp) * w.Hp * 2, 1024);
   w.bias2 = off;    off = align_up(off + static_cast<size_t>(w.Vp) * 4, 1024);
+  const size_t common = off;
+  w.scratch_tiles = have_hidden ? 0 : rb::joint_gemm_scratch_tiles(rb::device_sm_count());
+  w.h_scratch = off; off = align_up(off + static_cast<size_t>(w.scratch_tiles) * kTileM * w.Hp * 2, 1024);
   w.total_fwd = off;
+  off = common;      // the backward re-uses the region after the converted weights
   w.coef = off;     off = align_up(off + static_cast<size_t>(B) * T * U1 * 16, 1024);
   const size_t max_tiles = static_cast<size_t>(B) * ((T + rb::kTileT - 1) / rb::kTileT) * ((U1 + rb::kTileU - 1) / rb::kTileU);
   w.flags = off;    off = align_up(off + max_tiles, 1024);
   w.tile_list = off; off = align_up(off + max_tiles * sizeof(int), 1024);
   const size_t ring_rows = static_cast<size_t>(ring_tiles) * kTileM;
   w.g_ring = off;   off = align_up(off + ring_rows * w.Vp * 2, 1024);
-  w.h_ring = off;   off = align_up(off + ring_rows * w.Hp * 2, 1024);
+  w.h_ring = off;   off = align_up(off + (have_hidden ? 0 : ring_rows * w.Hp * 2), 1024);
   w.total_bwd = off;
   return w;
 }
@@ -68,20 +74,26 @@ int64_t rnnt_b200_max_tiles(int B, int T, int U1) {
   return static_cast<int64_t>(B) * ((T + rb::kTileT - 1) / rb::kTileT) * ((U1 + rb::kTileU - 1) / rb::kTileU);
 }
 
-int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, size_t* fwd_bytes,
-                              size_t* bwd_bytes) {
+size_t rnnt_b200_hidden_bytes(int B, int T, int U1, int H) {
+  if (B <= 0 || T <= 0 || U1 <= 0 || H <= 0) return 0;
+  return static_cast<size_t>(rnnt_b200_max_tiles(B, T, U1)) * kTileM * round_up(H, 64) * 2;
+}
+
+int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
+                              size_t* fwd_bytes, size_t* bwd_bytes) {
   RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && H > 0 && V > 1 && ring_tiles >= 0, -1, "invalid shape");
-  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, have_hidden != 0);
   if (fwd_bytes) *fwd_bytes = w.total_fwd;
   if (bwd_bytes) *bwd_bytes = w.total_bwd;
   return 0;
 }
 
-int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int64_t* offsets, int* Hp,
-                              int* Vp) {
-  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
+int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
+                              int64_t* offsets, int* Hp, int* Vp) {
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, have_hidden != 0);
   offsets[0] = w.tile_off; offsets[1] = w.wb; offsets[2] = w.bias2; offsets[3] = w.coef;
-  offsets[4] = w.g_ring; offsets[5] = w.h_ring; offsets[6] = w.total_bwd; offsets[7] = w.tile_list;
+  offsets[4] = w.g_ring; offsets[5] = have_hidden ? -1 : static_cast<int64_t>(w.h_ring);
+  offsets[6] = std::max(w.total_fwd, w.total_bwd); offsets[7] = w.tile_list;
   if (Hp) *Hp = w.Hp;
   if (Vp) *Vp = w.Vp;
   return 0;
@@ -96,12 +108,13 @@ int rnnt_b200_lattice(const float* lp, const int32_t* T_len, const int32_t* U_le
 int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, float* costs, float* lp, float* lse,
-                             float* alpha, float* beta, int32_t* status, void* workspace, size_t workspace_bytes,
-                             void* stream_) {
+                             float* alpha, float* beta, void* hidden, int32_t* status, void* workspace,
+                             size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
   if (rc) return rc;
-  const WsLayout w = ws_layout(B, T, U1, H, V, 0);
+  const WsLayout w = ws_layout(B, T, U1, H, V, 0, hidden != nullptr);
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 127) == 0, -3, "hidden must be 128-byte aligned");
   RB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total_fwd, -7, "workspace too small: need %zu bytes",
              w.total_fwd);
   RB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7, "workspace must be 256-byte aligned");
@@ -115,8 +128,16 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   rc = rb::launch_convert_weights(W, bias, V, H, w.Vp, w.Hp, Wb, bias2, stream);
   if (rc) return rc;
 
-  CUtensorMap tmW;
+  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
+  const int grid = static_cast<int>(std::min<int64_t>(rb::device_sm_count(), max_tiles));
+  // activation rows h = tanh(enc+pred): the caller's residual buffer (one 128-row block per lattice tile) or a
+  // small per-CTA scratch when no backward will follow
+  __half* hbuf = hidden ? static_cast<__half*>(hidden) : reinterpret_cast<__half*>(ws + w.h_scratch);
+  const uint64_t hrows = static_cast<uint64_t>(hidden ? max_tiles : w.scratch_tiles) * kTileM;
+  CUtensorMap tmW, tmH;
   rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmH, hbuf, 2, w.Hp, hrows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
 
   rb::JointArgs a{};
@@ -128,9 +149,8 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   a.tile_begin = 0; a.tile_cap = 0x3fffffff; a.tile_list = nullptr; a.n_active = nullptr;
   { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
-  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
-  const int grid = static_cast<int>(std::min<int64_t>(rb::device_sm_count(), max_tiles));
-  rc = rb::launch_joint_gemm(0, tmW, tmW, tmW, a, grid, stream);
+  a.h_out = hbuf; a.h_map = hidden ? 0 : 2; a.g_ring = nullptr;
+  rc = rb::launch_joint_gemm(0, true, tmW, tmH, a, grid, stream);
   if (rc) return rc;
   return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
 }
@@ -138,17 +158,18 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
 int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
-                             const float* alpha, const float* beta, const float* dcost, float clamp, float* d_enc,
-                             float* d_pred, float* dW, float* dbias, int64_t ring_tiles, int flags, void* workspace,
-                             size_t workspace_bytes, void* stream_) {
+                             const float* alpha, const float* beta, const void* hidden, const float* dcost,
+                             float clamp, float* d_enc, float* d_pred, float* dW, float* dbias, int64_t ring_tiles,
+                             int flags, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
   if (rc) return rc;
   RB_REQUIRE(ring_tiles >= 1 && ring_tiles * kTileM < (1ll << 30), -8, "ring_tiles out of range");
   RB_REQUIRE(H % 4 == 0, -2, "hidden_features must be a multiple of 4");
-  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles);
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, hidden != nullptr);
   RB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total_bwd, -7, "workspace too small: need %zu bytes",
              w.total_bwd);
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 127) == 0, -3, "hidden must be 128-byte aligned");
   RB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7, "workspace must be 256-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   int* tile_off = reinterpret_cast<int*>(ws + w.tile_off);
@@ -156,14 +177,18 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   float* bias2 = reinterpret_cast<float*>(ws + w.bias2);
   float4* coef = reinterpret_cast<float4*>(ws + w.coef);
   __half* g_ring = reinterpret_cast<__half*>(ws + w.g_ring);
-  __half* h_ring = reinterpret_cast<__half*>(ws + w.h_ring);
+  // activations: the forward's residual buffer (rows = lattice tile * 128) or, recomputed, a ring like g's
+  __half* h_src = hidden ? const_cast<__half*>(static_cast<const __half*>(hidden))
+                         : reinterpret_cast<__half*>(ws + w.h_ring);
   const uint64_t ring_rows = static_cast<uint64_t>(ring_tiles) * kTileM;
+  const int h_map = hidden ? 0 : 1;
 
   RB_CUDA_CHECK(cudaMemsetAsync(d_enc, 0, static_cast<size_t>(B) * T * H * 4, stream));
   RB_CUDA_CHECK(cudaMemsetAsync(d_pred, 0, static_cast<size_t>(B) * U1 * H * 4, stream));
   RB_CUDA_CHECK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * 4, stream));
   RB_CUDA_CHECK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream));
 
+  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
   float* gscale = reinterpret_cast<float*>(tile_off + B + 2);
   rc = rb::launch_tile_table(T_len, U_len, B, T, U1, tile_off, nullptr, dcost, gscale, stream);
   if (rc) return rc;
@@ -171,29 +196,28 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
   rc = rb::launch_coef(lp, lse, alpha, beta, dcost, gscale, T_len, U_len, B, T, U1, coef, stream);
   if (rc) return rc;
-  const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
   int* n_active = tile_off + B + 4;
   int* tile_list = reinterpret_cast<int*>(ws + w.tile_list);
   rc = rb::launch_tile_activity(coef, T_len, U_len, tile_off, B, T, U1, max_tiles, (flags & 1) ? 1 : 0,
                                 reinterpret_cast<unsigned char*>(ws + w.flags), tile_list, n_active, stream);
   if (rc) return rc;
 
-  CUtensorMap tmW, tmWmn, tmGst, tmG256, tmHst, tmGmn, tmHmn;
+  const uint64_t h_rows = hidden ? static_cast<uint64_t>(max_tiles) * kTileM : ring_rows;
+  CUtensorMap tmW, tmWmn, tmG256, tmHk, tmGmn, tmHmn;
   // W [Vp, Hp]: K-major boxes (64 k x 256 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
   rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmWmn, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
-  // rings: 64 x 128 boxes for the tile stores and the K-major dh operand, 64 x 64 boxes for the MN-major dW operands
-  rc = rb::make_tmap_2d(&tmGst, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 128);
-  if (rc) return rc;
-  rc = rb::make_tmap_2d(&tmHst, h_ring, 2, w.Hp, ring_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
+  // activations: 64 x 128 K-major boxes for the logit recompute, 64 x 64 boxes for the MN-major dW operand;
+  // gradient ring: 64 x 256 K-major boxes for dh, 64 x 64 boxes for the MN-major dW operand
+  rc = rb::make_tmap_2d(&tmHk, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmG256, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 256);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmGmn, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 64);
   if (rc) return rc;
-  rc = rb::make_tmap_2d(&tmHmn, h_ring, 2, w.Hp, ring_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
+  rc = rb::make_tmap_2d(&tmHmn, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
 
   const int sms = rb::device_sm_count();
@@ -212,7 +236,8 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles); a.tile_list = tile_list; a.n_active = n_active;
     { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
-    rc = rb::launch_joint_gemm(1, tmW, tmGst, tmHst, a, grid, stream);
+    a.h_out = h_src; a.h_map = h_map; a.g_ring = g_ring;
+    rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, a, grid, stream);
     if (rc) return rc;
 
     rb::DhArgs d{};
@@ -227,7 +252,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     if (rc) return rc;
 
     rb::DwArgs g{};
-    g.n_active = n_active; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
+    g.n_active = n_active; g.tile_list = tile_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
     g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW; g.db = dbias; g.gscale = gscale;
     const int out_tiles = (w.Vp / kTileM) * ((((w.Hp + 255) / 256) + 1) / 2);
     const int64_t kchunks = chunk_tiles * 2;

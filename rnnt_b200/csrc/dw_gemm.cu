@@ -81,6 +81,10 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           tma_load_2d(a_ring + sa * kBytesA + j * 8192, &tmGmn, a_full + 8 * sa, vt * kTileM + j * 64, kc * kBK);
+        // activation rows of this 64-cell chunk: ring rows, or the forward's residual buffer (tile-indexed)
+        const int hrow = (p.h_map == 0)
+                             ? __ldg(p.tile_list + p.tile_begin + (kc >> 1)) * kTileM + (kc & 1) * kBK
+                             : kc * kBK;
         for (int blk = 0; blk < nblk; ++blk, ++itb) {
           const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
           mbar_wait(b_empty + 8 * sb, phb ^ 1);
@@ -88,7 +92,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             tma_load_2d(b_ring + sb * kBytesB + j * 8192, &tmHmn, b_full + 8 * sb,
-                        (ht * 2 + blk) * kBN + j * 64, kc * kBK);
+                        (ht * 2 + blk) * kBN + j * 64, hrow);
         }
       }
     }

@@ -1,4 +1,4 @@
-// Fused joint GEMM kernel (forward "F" and backward-recompute "G" modes).
+// Fused joint GEMM kernel (forward "F" and backward "G" modes).
 //
 // Replaces rnnt/joint.py:32-39 (broadcast add + tanh + joint_ln) fused with the first half of
 // torchaudio's rnnt_loss (ReduceMax2D / ReduceLogSumExpGivenMax2D / ComputeLogProbs, reference call
@@ -9,74 +9,66 @@
 // (fp16 operands: tanh output lies in [-1,1] and joint weights are O(1), so fp16's 11-bit mantissa gives 8x
 // finer rounding than bf16 at the same tensor-core rate; accumulation is fp32 in TMEM.)
 //
-// Warp roles (480 threads, 1 CTA / SM, persistent over 16(t)x8(u) lattice tiles):
-//   warp 0      TMA producer: W tiles (256 rows x 64 k, 128B-swizzled) into a 4-stage ring
-//   warp 1      tcgen05.mma issuer (M=128, N=256, K=16; two 256-column accumulators per N pass)
-//   warps 2-5   epilogue: tcgen05.ld -> online log-sum-exp + blank/label gather (F) or
-//               softmax*gamma - one-hots -> fp16 (scaled by S) -> smem -> TMA store into the gradient ring (G)
-//   warps 6-13  A-operand producers: tanh(enc+pred) -> fp16 -> swizzled smem (4-stage ring)
-//   warp 14     (G mode) TMA-stores each finished A stage into the hidden-activation ring
+// Structure (1 persistent CTA / SM, work unit = 16(t) x 8(u) lattice tile = 128 GEMM rows):
+//   * The hidden activations h = tanh(enc+pred) of a tile are produced ONCE, as fp16 rows of a global buffer
+//     (the residual the backward re-uses, or a small per-CTA scratch), by 8 producer warps that run one to two
+//     tiles AHEAD of the tensor pipe.  They are decoupled from the MMA pipeline: no shared-memory staging, no
+//     per-chunk hand-off, their MUFU/ALU work hides under the MMAs of the previous tile.
+//   * The GEMM itself is a plain TMA-fed tcgen05 pipeline: per (pass, k-chunk) one 256x64 W box and one 128x64 h box
+//     (just written, so an L2 hit) land in a 4-stage ring; a pass is one 256-column accumulator, and the two halves
+//     of TMEM ping-pong so that the epilogue of pass i overlaps the MMAs of pass i+1.
+//   * G mode with saved activations needs no producers at all.
+//
+// Warp roles: 0 TMA loader | 1 tcgen05.mma issuer | 2-9 epilogue (set e = warps 2+4e..5+4e drains accumulator e)
+//             | 10-17 (PRODUCE only) activation producers
 #include "common.cuh"
 #include "kernels.h"
-
-#ifndef RNNT_G_STAGES_A
-#define RNNT_G_STAGES_A 2
-#define RNNT_G_STAGES_B 4
-#endif
 
 namespace rb {
 
 namespace {
 
-// Shared-memory budget (227 KB): the W-tile (B operand) ring is the latency-critical one (TMA round trip ~1 us
-// vs 0.26 us of MMA work per 32 KB stage), the computed A operand only needs double buffering.
-template <int MODE> struct StagesA { static constexpr int value = MODE == 0 ? 4 : RNNT_G_STAGES_A; };
-template <int MODE> struct StagesB { static constexpr int value = MODE == 0 ? 4 : RNNT_G_STAGES_B; };
-constexpr int kBytesA = kTileM * kBK * 2;  // 16 KB
-constexpr int kBytesB = kBN * kBK * 2;     // 32 KB
-constexpr int kBytesG = kTileM * 64 * 2;   // 16 KB staging box for the gradient ring store
-constexpr int kNumThreads = 608;
-constexpr int kFirstEpiWarp = 2;      // warps 2-5: epilogue set 0 (accumulator 0), warps 6-9: set 1 (accumulator 1)
+constexpr int kStages = 4;
+constexpr int kBytesA = kTileM * kBK * 2;  // 16 KB: 128 cells x 64 k
+constexpr int kBytesB = kBN * kBK * 2;     // 32 KB: 256 classes x 64 k
+constexpr int kStageBytes = kBytesA + kBytesB;
+constexpr int kFirstEpiWarp = 2;
 constexpr int kNumEpiWarps = 8;
 constexpr int kFirstProdWarp = 10;
 constexpr int kNumProdWarps = 8;
-constexpr int kStoreWarp = 18;
+constexpr int kThreadsNoProd = 32 * kFirstProdWarp;                     // 320
+constexpr int kThreadsProd = 32 * (kFirstProdWarp + kNumProdWarps);     // 576
 constexpr int kTmemCols = 512;
+constexpr int kScratchSlots = 4;   // per-CTA activation scratch (h_map 2): tiles in flight <= 3
 
-template <int MODE>
 struct SmemLayout {
-  // offsets from the 1024-aligned base
-  static constexpr int b_ring = 0;
-  static constexpr int a_ring = b_ring + StagesB<MODE>::value * kBytesB;
-  static constexpr int g_stage = a_ring + StagesA<MODE>::value * kBytesA;
-  static constexpr int xchg = g_stage + (MODE == 1 ? 4 * kBytesG : 0);     // F: set-1 -> set-0 softmax partials
-  static constexpr int bars = xchg + (MODE == 0 ? 2 * kTileM * 16 : 0);
+  static constexpr int ring = 0;
+  static constexpr int xchg = ring + kStages * kStageBytes;   // F: set-1 -> set-0 softmax partials (2 x 128 x 16 B)
+  static constexpr int bars = xchg + 2 * kTileM * 16;
   static constexpr int total = bars + 256;
 };
 
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 }  // namespace
 
-size_t joint_gemm_smem_bytes() { return SmemLayout<0>::total + 1024; }
+size_t joint_gemm_smem_bytes() { return SmemLayout::total + 1024; }
+int joint_gemm_scratch_tiles(int grid) { return grid * kScratchSlots; }
 
-template <int MODE>  // 0 = forward (lse + gather), 1 = backward recompute (gradient ring)
-__global__ void __launch_bounds__(kNumThreads, 1)
-joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmG,
-                  const __grid_constant__ CUtensorMap tmHr, JointArgs p) {
+template <int MODE, bool PRODUCE>  // MODE 0 = forward (lse + gather), 1 = backward (gradient ring)
+__global__ void __launch_bounds__(PRODUCE ? kThreadsProd : kThreadsNoProd, 1)
+joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, JointArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  using SL = SmemLayout<MODE>;
-  constexpr int kStagesB = StagesB<MODE>::value;
-  constexpr int kStagesA = StagesA<MODE>::value;
+  using SL = SmemLayout;
 
-  const uint32_t b_ring = smem_base + SL::b_ring;
-  const uint32_t a_ring = smem_base + SL::a_ring;
-  const uint32_t g_stage = smem_base + SL::g_stage;
+  const uint32_t ring = smem_base + SL::ring;
   const uint32_t bars = smem_base + SL::bars;
   // barrier map (8 bytes each)
-  const uint32_t b_full = bars, b_empty = bars + 8 * kStagesB;
-  const uint32_t a_full = bars + 16 * kStagesB, a_empty = a_full + 8 * kStagesA;
-  const uint32_t tmem_full = a_empty + 8 * kStagesA, tmem_empty = tmem_full + 8;
+  const uint32_t full = bars, empty = bars + 8 * kStages;
+  const uint32_t tmem_full = bars + 16 * kStages, tmem_empty = tmem_full + 16;
+  const uint32_t h_ready = tmem_empty + 16, tile_done = h_ready + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SL::bars + 200);
 
   const int warp = threadIdx.x >> 5;
@@ -85,25 +77,28 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const int total_tiles = p.n_active ? __ldg(p.n_active) : __ldg(p.tile_off + p.B);
   const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots [tile_begin, tile_end)
   const int nk = p.Hp / kBK;
-  const int nblk_total = p.Vp / kBN;
-  const int npass = (nblk_total + 1) / 2;
+  const int npass = p.Vp / kBN;
+
+  // row block of the activation buffer that holds the tile of work-list slot `slot` (the cnt-th tile of this CTA)
+  auto h_row0 = [&](int slot, int tile, uint32_t cnt) -> int {
+    if (p.h_map == 0) return tile * kTileM;                       // full buffer, indexed by lattice tile
+    if (p.h_map == 1) return (slot - p.tile_begin) * kTileM;      // backward ring, indexed by slot of this chunk
+    return (static_cast<int>(blockIdx.x) * kScratchSlots + static_cast<int>(cnt % kScratchSlots)) * kTileM;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
-    if (MODE == 1) {
-      tma_prefetch_desc(&tmG);
-      tma_prefetch_desc(&tmHr);
+    tma_prefetch_desc(&tmH);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, 1);
     }
-    for (int s = 0; s < kStagesB; ++s) {
-      mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full + 8 * a, 1);
+      mbar_init(tmem_empty + 8 * a, kNumEpiWarps / 2);
+      mbar_init(h_ready + 8 * a, kNumProdWarps);
+      mbar_init(tile_done + 8 * a, 1);
     }
-    for (int s = 0; s < kStagesA; ++s) {
-      mbar_init(a_full + 8 * s, kNumProdWarps);
-      mbar_init(a_empty + 8 * s, MODE == 1 ? 2 : 1);
-    }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, kNumEpiWarps);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -116,19 +111,23 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer (W tiles)
+    // ===================================================================== TMA loader (W boxes + activation boxes)
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
+      uint32_t it = 0, cnt = 0;
+      for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++cnt) {
+        const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
+        const int row0 = h_row0(slot, tile, cnt);
+        if (PRODUCE) {
+          mbar_wait(h_ready + 8 * (cnt & 1), (cnt >> 1) & 1);
+          fence_proxy_async_all();   // the producers' generic-proxy global stores -> TMA (async proxy) reads
+        }
         for (int pass = 0; pass < npass; ++pass) {
-          const int nblk = min(2, nblk_total - pass * 2);
-          for (int kc = 0; kc < nk; ++kc) {
-            for (int blk = 0; blk < nblk; ++blk, ++it) {
-              const uint32_t s = it % kStagesB, ph = (it / kStagesB) & 1;
-              mbar_wait(b_empty + 8 * s, ph ^ 1);
-              mbar_expect_tx(b_full + 8 * s, kBytesB);
-              tma_load_2d(b_ring + s * kBytesB, &tmW, b_full + 8 * s, kc * kBK, (pass * 2 + blk) * kBN);
-            }
+          for (int kc = 0; kc < nk; ++kc, ++it) {
+            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+            mbar_wait(empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(full + 8 * s, kStageBytes);
+            tma_load_2d(ring + s * kStageBytes, &tmW, full + 8 * s, kc * kBK, pass * kBN);
+            tma_load_2d(ring + s * kStageBytes + kBytesB, &tmH, full + 8 * s, kc * kBK, row0);
           }
         }
       }
@@ -136,48 +135,45 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     constexpr uint32_t idesc = make_idesc(kTileM, kBN, 0, 0, kFmtF16, kFmtF16);
-    uint32_t ita = 0, itb = 0, pc = 0;
-    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
+    uint32_t it = 0, pc = 0, cnt = 0;
+    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++cnt) {
       for (int pass = 0; pass < npass; ++pass, ++pc) {
-        const int nblk = min(2, nblk_total - pass * 2);
-        mbar_wait(tmem_empty, (pc & 1) ^ 1);
+        const uint32_t acc = pc & 1;
+        mbar_wait(tmem_empty + 8 * acc, ((pc >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < nk; ++kc, ++ita) {
-          const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
-          mbar_wait(a_full + 8 * sa, pha);
-          for (int blk = 0; blk < nblk; ++blk, ++itb) {
-            const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
-            mbar_wait(b_full + 8 * sb, phb);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = a_ring + sa * kBytesA, b_addr = b_ring + sb * kBytesB;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(full + 8 * s, ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t b_addr = ring + s * kStageBytes, a_addr = b_addr + kBytesB;
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-                const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-                umma_f16(tmem_base + blk * kBN, ad, bd, idesc, (kc | k) != 0);
-              }
-              umma_commit(b_empty + 8 * sb);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_f16(tmem_base + acc * kBN, ad, bd, idesc, (kc | k) != 0);
             }
-            __syncwarp();
+            umma_commit(empty + 8 * s);
           }
-          if (lane == 0) umma_commit(a_empty + 8 * sa);
           __syncwarp();
         }
-        if (lane == 0) umma_commit(tmem_full);
+        if (lane == 0) umma_commit(tmem_full + 8 * acc);
+        __syncwarp();
+      }
+      if (PRODUCE) {
+        if (lane == 0) umma_commit(tile_done + 8 * (cnt & 1));   // this tile's activation rows are consumed
         __syncwarp();
       }
     }
   } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kNumEpiWarps) {
     // ===================================================================== epilogue
-    // Two epilogue sets work in parallel: set e drains accumulator e (256 columns) of every pass.
+    // Set e drains accumulator e, i.e. every pass with (global pass counter & 1) == e.
     const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
     const int eset = (warp - kFirstEpiWarp) >> 2;
     const int row = lane_grp * 32 + lane;
     const int ti = row >> 3, ui = row & 7;
-    const int set_tid = ((warp - kFirstEpiWarp) & 3) * 32 + lane;
     float4* xchg = reinterpret_cast<float4*>(smem_gen + SL::xchg);
-    uint32_t pc = 0, box_count = 0, tcount = 0;
+    uint32_t pc = 0, tcount = 0;
     for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++tcount) {
       const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
@@ -195,15 +191,17 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         gam = c4.x; eB = c4.y; eE = c4.z; lse2 = c4.w * kLog2e;
         if (p.clamp > 0.f) cbound = p.clamp * fabsf(p.dcost ? __ldg(p.dcost + tc.b) : 1.f) * __ldg(p.gscale);
       }
-      const int ring_row0 = (slot - p.tile_begin) * kTileM;
+      __half* g_row = nullptr;
+      if (MODE == 1)
+        g_row = p.g_ring + (static_cast<long long>(slot - p.tile_begin) * kTileM + row) * p.Vp;
 
       for (int pass = 0; pass < npass; ++pass, ++pc) {
-        const int nblk = min(2, nblk_total - pass * 2);
-        mbar_wait(tmem_full, pc & 1);
+        if (static_cast<int>(pc & 1) != eset) continue;
+        mbar_wait(tmem_full + 8 * eset, (pc >> 1) & 1);
         tc_fence_after();
-        const int nchunk = ((p.dbg & 1) || eset >= nblk) ? 0 : (kBN / 32);
+        const int nchunk = (p.dbg & 1) ? 0 : (kBN / 32);
         for (int c32 = 0; c32 < nchunk; ++c32) {
-          const int col0 = (pass * 2 + eset) * kBN + c32 * 32;  // global column of v[0]
+          const int col0 = pass * kBN + c32 * 32;  // global column of v[0]
           float v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + eset * kBN + c32 * 32, v);
           tmem_ld_wait();
@@ -250,48 +248,31 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -cbound), cbound);
             }
-            // stage fp16 into this set's 128 x 64 swizzled box (two 32-column halves per box)
-            const uint32_t buf = g_stage + (eset * 2 + (box_count & 1)) * kBytesG;
-            if ((c32 & 1) == 0) {
-              // the TMA store that last used this buffer (two boxes ago) must have finished reading it
-              if (set_tid == 0) tma_store_wait_read<1>();
-              named_bar_sync(1 + eset, 128);
-            }
+            // fp16 (scaled by S through the coefficients) straight to the gradient ring: 64 contiguous bytes per row
+            uint4* dst = reinterpret_cast<uint4*>(g_row + col0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint32_t w0 = pack_f16x2(v[8 * q + 0], v[8 * q + 1]);
-              const uint32_t w1 = pack_f16x2(v[8 * q + 2], v[8 * q + 3]);
-              const uint32_t w2 = pack_f16x2(v[8 * q + 4], v[8 * q + 5]);
-              const uint32_t w3 = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
-              const uint32_t chunk = (c32 & 1) * 4 + q;
-              const uint32_t addr = buf + row * 128 + ((chunk ^ (row & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2),
-                           "r"(w3)
-                           : "memory");
-            }
-            if ((c32 & 1) == 1) {
-              fence_proxy_async();
-              named_bar_sync(1 + eset, 128);
-              if (set_tid == 0) {
-                tma_store_2d(&tmG, buf, (pass * 2 + eset) * kBN + (c32 >> 1) * 64, ring_row0);
-                tma_store_commit();
-              }
-              ++box_count;
+              uint4 w;
+              w.x = pack_f16x2(v[8 * q + 0], v[8 * q + 1]);
+              w.y = pack_f16x2(v[8 * q + 2], v[8 * q + 3]);
+              w.z = pack_f16x2(v[8 * q + 4], v[8 * q + 5]);
+              w.w = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
+              dst[q] = w;
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
+        if (lane == 0) mbar_arrive(tmem_empty + 8 * eset);
       }
       if (MODE == 0) {
         // combine the two sets' online-softmax partials: set 1 -> smem -> set 0 writes lp / lse
-        float4* slot = xchg + (tcount & 1) * kTileM + row;
-        if (eset == 1) *slot = make_float4(m, ssum, x_tgt, x_blank);
-        named_bar_sync(3, 256);
+        float4* xs = xchg + (tcount & 1) * kTileM + row;
+        if (eset == 1) *xs = make_float4(m, ssum, x_tgt, x_blank);
+        named_bar_sync(3, 32 * kNumEpiWarps);
         if (eset == 0 && valid && !(p.dbg & 1)) {
-          const float4 o = *slot;
-          const float mm = fmaxf(m, o.x);
+          const float4 o = *xs;
+          const float mm = fmaxf(m, o.x);   // finite: every tile has at least one pass
           const float stot = ssum * ex2_approx(m - mm) + o.y * ex2_approx(o.x - mm);
           const float l2 = mm + lg2_approx(stot);
           p.lse[cell] = l2 * kLn2;
@@ -302,19 +283,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
       }
     }
-    if (MODE == 1 && set_tid == 0) tma_store_wait_all<0>();
-  } else if (warp >= kFirstProdWarp && warp < kFirstProdWarp + kNumProdWarps) {
-    // ===================================================================== A producers
+  } else if (PRODUCE && warp >= kFirstProdWarp) {
+    // ===================================================================== activation producers
     // Warp rg produces rows rg*16 .. rg*16+15 of the tile (t-rows 2rg, 2rg+1; all 8 u).  Lane l owns the 16-byte
-    // column chunk c = l & 7 (8 hidden units) of the four rows rs, rs+4, rs+8, rs+12 (rs = l >> 3), i.e. the pairs
-    // (t-row 0|1) x (u = rs | rs+4): 4 x 8 inputs, 32 tanh, four 16-byte shared stores.  Few wide stores matter:
-    // fence.proxy.async is a MEMBAR.ALL.CTA whose latency grows with the number of shared stores in flight.
+    // column chunk c = l & 7 (8 hidden units) of the four rows (t-row 0|1) x (u = rs | rs+4), rs = l >> 3:
+    // 4 x 8 inputs -> 32 tanh -> four 16-byte global stores; the 8 lanes of one row write 128 contiguous bytes.
     const int rg = warp - kFirstProdWarp;
     const int c = lane & 7, rs = lane >> 3;
-    uint32_t it = 0;
-    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
+    uint32_t cnt = 0;
+    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++cnt) {
       const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
+      const int row0 = h_row0(slot, tile, cnt);
       const float* e_ptr[2];
       const float* p_ptr[2];
 #pragma unroll
@@ -341,58 +321,41 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
       };
       load_chunk(0, e_cur, p_cur);
-      for (int pass = 0; pass < npass; ++pass) {
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
-          mbar_wait(a_empty + 8 * s, ph ^ 1);
-          const uint32_t stage = a_ring + s * kBytesA;
-          if (!(p.dbg & 2)) {
+      // stay at most two tiles ahead of the tensor pipe: tile cnt-2 must be fully consumed (also keeps the
+      // two-phase h_ready / tile_done barriers and the 4-slot scratch unambiguous)
+      if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
+      __half* out_base = p.h_out + static_cast<long long>(row0 + rg * 16) * p.Hp + 8 * c;
+      for (int kc = 0; kc < nk; ++kc) {
+        uint4 w[2][2];
+        if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {        // t-row
+          for (int i = 0; i < 2; ++i) {        // t-row
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {      // u = rs + 4j
-                const float4 a0 = e_cur[i][0], a1 = e_cur[i][1], b0 = p_cur[j][0], b1 = p_cur[j][1];
-                const uint32_t w0 = pack_f16x2(tanh_approx(a0.x + b0.x), tanh_approx(a0.y + b0.y));
-                const uint32_t w1 = pack_f16x2(tanh_approx(a0.z + b0.z), tanh_approx(a0.w + b0.w));
-                const uint32_t w2 = pack_f16x2(tanh_approx(a1.x + b1.x), tanh_approx(a1.y + b1.y));
-                const uint32_t w3 = pack_f16x2(tanh_approx(a1.z + b1.z), tanh_approx(a1.w + b1.w));
-                const int ui = rs + 4 * j;                       // = row & 7
-                const int r = rg * 16 + i * 8 + ui;
-                const uint32_t addr = stage + r * 128 + ((static_cast<uint32_t>(c) ^ static_cast<uint32_t>(ui)) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                             : "memory");
-              }
+            for (int j = 0; j < 2; ++j) {      // u = rs + 4j
+              const float4 a0 = e_cur[i][0], a1 = e_cur[i][1], b0 = p_cur[j][0], b1 = p_cur[j][1];
+              w[i][j].x = pack_f16x2(tanh_approx(a0.x + b0.x), tanh_approx(a0.y + b0.y));
+              w[i][j].y = pack_f16x2(tanh_approx(a0.z + b0.z), tanh_approx(a0.w + b0.w));
+              w[i][j].z = pack_f16x2(tanh_approx(a1.x + b1.x), tanh_approx(a1.y + b1.y));
+              w[i][j].w = pack_f16x2(tanh_approx(a1.z + b1.z), tanh_approx(a1.w + b1.w));
             }
           }
-          // the inputs of the next chunk are requested now (their registers are free again); the fence, the barrier
-          // hand-off and the other producer warp of this scheduler cover the load latency
-          if (kc + 1 < nk || pass + 1 < npass) load_chunk((kc + 1 < nk) ? kc + 1 : 0, e_cur, p_cur);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(a_full + 8 * s);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) w[i][j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
         }
+        // the inputs of the next chunk are requested before the stores of this one are issued
+        if (kc + 1 < nk) load_chunk(kc + 1, e_cur, p_cur);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            *reinterpret_cast<uint4*>(out_base + static_cast<long long>(i * 8 + rs + 4 * j) * p.Hp + kc * kBK) = w[i][j];
       }
-    }
-  } else if (warp == kStoreWarp) {
-    // ===================================================================== hidden-ring store (G mode)
-    if (MODE == 1 && lane == 0) {
-      uint32_t it = 0;
-      for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x) {
-        const int ring_row0 = (slot - p.tile_begin) * kTileM;
-        for (int pass = 0; pass < npass; ++pass) {
-          for (int kc = 0; kc < nk; ++kc, ++it) {
-            const uint32_t s = it % kStagesA, ph = (it / kStagesA) & 1;
-            mbar_wait(a_full + 8 * s, ph);
-            if (pass == 0) {
-              tma_store_2d(&tmHr, a_ring + s * kBytesA, kc * kBK, ring_row0);
-              tma_store_commit();
-              tma_store_wait_read<0>();
-            }
-            mbar_arrive(a_empty + 8 * s);
-          }
-        }
-      }
-      tma_store_wait_all<0>();
+      fence_proxy_async_all();   // generic-proxy global writes -> visible to the loader's TMA reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready + 8 * (cnt & 1));
     }
   }
 
@@ -404,17 +367,25 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   }
 }
 
-int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
-                      const JointArgs& args, int grid, cudaStream_t stream) {
+int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
+                      int grid, cudaStream_t stream) {
   ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
-  const size_t smem = (mode == 0 ? SmemLayout<0>::total : SmemLayout<1>::total) + 1024;
+  const size_t smem = SmemLayout::total + 1024;
+#define RB_LAUNCH_JG(M, P)                                                                                         \
+  do {                                                                                                             \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                       (int)smem));                                                                \
+    joint_gemm_kernel<M, P><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, args);            \
+  } while (0)
   if (mode == 0) {
-    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_gemm_kernel<0><<<grid, kNumThreads, smem, stream>>>(tmW, tmG, tmHr, args);
+    RB_REQUIRE(produce, -30, "forward joint kernel always produces the activations");
+    RB_LAUNCH_JG(0, true);
+  } else if (produce) {
+    RB_LAUNCH_JG(1, true);
   } else {
-    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    joint_gemm_kernel<1><<<grid, kNumThreads, smem, stream>>>(tmW, tmG, tmHr, args);
+    RB_LAUNCH_JG(1, false);
   }
+#undef RB_LAUNCH_JG
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

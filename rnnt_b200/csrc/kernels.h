@@ -32,6 +32,10 @@ struct JointArgs {
   const float* dcost;     // G: (B) or nullptr (only used to scale the clamp bound)
   const float* gscale;    // G: {S, 1/S} power-of-two gradient scale
   float clamp;            // G: <= 0 disables (torchaudio's clamp argument, rnnt/model.py:40 passes -1)
+  __half* h_out;          // producers: activation rows h = tanh(enc+pred) as fp16 [rows, Hp] (same buffer tmH reads)
+  int h_map;              // row block of a tile in that buffer: 0 = tile*128 (saved residual), 1 = ring slot*128
+                          // (backward recompute), 2 = per-CTA scratch slot (forward without a residual buffer)
+  __half* g_ring;         // G: gradient ring [ring_tiles*128, Vp] fp16
   int dbg;                // diagnostics only (RNNT_B200_DBG): 1 = skip epilogue math, 2 = skip producer math
 };
 
@@ -54,6 +58,8 @@ struct DhArgs {
 
 struct DwArgs {
   const int* n_active;   // number of work-list slots (ring rows of this chunk = slots in range * 128)
+  const int* tile_list;  // slot -> lattice tile (row block of the saved activations when h_map == 0)
+  int h_map;             // 0 = activations come from the forward's residual buffer (rows tile*128), 1 = from the ring
   const int* tile_off;
   int B, H, Hp, V, Vp;
   int tile_begin, tile_cap;
@@ -86,8 +92,9 @@ size_t greedy_decode_scratch_bytes(int B, int H, int V, int E);
 int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream);
 
 size_t joint_gemm_smem_bytes();
-int launch_joint_gemm(int mode, const CUtensorMap& tmW, const CUtensorMap& tmG, const CUtensorMap& tmHr,
-                      const JointArgs& args, int grid, cudaStream_t stream);
+int joint_gemm_scratch_tiles(int grid);   // tiles of per-CTA activation scratch the forward needs when h_map == 2
+int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
+                      int grid, cudaStream_t stream);
 int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, int grid,
                    cudaStream_t stream);
 int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream);

@@ -15,6 +15,9 @@ import torch
 from . import _lib
 
 _DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(1 << 30)))
+# Keep h = tanh(enc + pred) (fp16, 2*H bytes per lattice cell) from the forward for the backward (default), or
+# recompute it there (RNNT_B200_SAVE_HIDDEN=0: residuals shrink to 20 bytes per cell, the backward runs ~10 % slower).
+_SAVE_HIDDEN = os.environ.get("RNNT_B200_SAVE_HIDDEN", "1") != "0"
 
 # Optional bookkeeping for bench.py / tests: when enabled, every fused backward leaves a 2-element device tensor
 # (active lattice tiles, total lattice tiles) here.  Off by default (costs two tiny copies per step).
@@ -60,22 +63,23 @@ def _check_index_tensors(targets, logit_lengths, target_lengths):
         raise RuntimeError("targets must be contiguous")
 
 
-def pick_ring_tiles(B: int, T: int, U1: int, H: int, V: int, ring_bytes: Optional[int] = None) -> int:
+def pick_ring_tiles(B: int, T: int, U1: int, H: int, V: int, ring_bytes: Optional[int] = None,
+                    have_hidden: bool = False) -> int:
     """Tiles per backward chunk: the batch's tile bound split into equal chunks of at most `ring_bytes`."""
     ring_bytes = _DEFAULT_RING_BYTES if ring_bytes is None else ring_bytes
     max_tiles = int(_lib.lib().rnnt_b200_max_tiles(B, T, U1))
     hp = (H + 63) // 64 * 64
     vp = (V + 255) // 256 * 256
-    per_tile = 128 * (hp + vp) * 2
+    per_tile = 128 * (vp if have_hidden else hp + vp) * 2
     cap = max(1, ring_bytes // per_tile)
     nchunks = (max_tiles + cap - 1) // cap
     return (max_tiles + nchunks - 1) // nchunks
 
 
-def workspace_bytes(B, T, U1, H, V, ring_tiles):
+def workspace_bytes(B, T, U1, H, V, ring_tiles, have_hidden=False):
     fwd, bwd = C.c_size_t(0), C.c_size_t(0)
-    _lib.check(_lib.lib().rnnt_b200_workspace_bytes(B, T, U1, H, V, ring_tiles, C.byref(fwd), C.byref(bwd)),
-               "workspace_bytes")
+    _lib.check(_lib.lib().rnnt_b200_workspace_bytes(B, T, U1, H, V, ring_tiles, int(bool(have_hidden)),
+                                                    C.byref(fwd), C.byref(bwd)), "workspace_bytes")
     return fwd.value, bwd.value
 
 
@@ -84,7 +88,7 @@ class _FusedJointLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, pred, weight, bias, targets, logit_lengths, target_lengths, blank, clamp, ring_bytes,
-                skip_zero_tiles=True):
+                skip_zero_tiles=True, save_hidden=None):
         L = _lib.lib()
         B, T, H = enc.shape
         U1 = pred.shape[1]
@@ -99,16 +103,22 @@ class _FusedJointLoss(torch.autograd.Function):
         lse = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
         alpha = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
         beta = torch.empty(B, T, U1, dtype=torch.float32, device=dev)
-        fwd_bytes, _ = workspace_bytes(B, T, U1, H, V, 0)
+        needs_grad = any(ctx.needs_input_grad[:4])
+        save_hidden = (_SAVE_HIDDEN if save_hidden is None else bool(save_hidden)) and needs_grad
+        hidden = (torch.empty(L.rnnt_b200_hidden_bytes(B, T, U1, H), dtype=torch.uint8, device=dev)
+                  if save_hidden else None)
+        fwd_bytes, _ = workspace_bytes(B, T, U1, H, V, 0, save_hidden)
         ws = torch.empty(fwd_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.rnnt_b200_joint_loss_fwd(
                 enc_c.data_ptr(), enc_c.stride(0), enc_c.stride(1), pred_c.data_ptr(), weight_c.data_ptr(),
                 bias_c.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
                 B, T, U1, H, V, blank, costs.data_ptr(), lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(),
-                beta.data_ptr(), None, ws.data_ptr(), fwd_bytes, _stream_ptr(dev)), "joint_loss_fwd")
+                beta.data_ptr(), hidden.data_ptr() if save_hidden else None, None, ws.data_ptr(), fwd_bytes,
+                _stream_ptr(dev)), "joint_loss_fwd")
         ctx.save_for_backward(enc_c, pred_c, weight_c, bias_c, targets, logit_lengths, target_lengths,
-                              lp, lse, alpha, beta)
+                              lp, lse, alpha, beta, *([hidden] if save_hidden else []))
+        ctx.have_hidden = save_hidden
         ctx.blank, ctx.clamp, ctx.ring_bytes = blank, clamp, ring_bytes
         ctx.flags = 0 if skip_zero_tiles else 1
         ctx.mark_non_differentiable(lp, lse, alpha, beta)
@@ -117,7 +127,8 @@ class _FusedJointLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dcost, *_unused):
         L = _lib.lib()
-        enc, pred, weight, bias, targets, logit_lengths, target_lengths, lp, lse, alpha, beta = ctx.saved_tensors
+        enc, pred, weight, bias, targets, logit_lengths, target_lengths, lp, lse, alpha, beta = ctx.saved_tensors[:11]
+        hidden = ctx.saved_tensors[11] if ctx.have_hidden else None
         B, T, H = enc.shape
         U1 = pred.shape[1]
         V = weight.shape[0]
@@ -127,21 +138,21 @@ class _FusedJointLoss(torch.autograd.Function):
         d_pred = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
         dW = torch.empty(V, H, dtype=torch.float32, device=dev)
         db = torch.empty(V, dtype=torch.float32, device=dev)
-        ring_tiles = pick_ring_tiles(B, T, U1, H, V, ctx.ring_bytes)
-        _, bwd_bytes = workspace_bytes(B, T, U1, H, V, ring_tiles)
+        ring_tiles = pick_ring_tiles(B, T, U1, H, V, ctx.ring_bytes, ctx.have_hidden)
+        _, bwd_bytes = workspace_bytes(B, T, U1, H, V, ring_tiles, ctx.have_hidden)
         ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.rnnt_b200_joint_loss_bwd(
                 enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), weight.data_ptr(), bias.data_ptr(),
                 targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(), B, T, U1, H, V, ctx.blank,
-                lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(), dcost.data_ptr(),
-                float(ctx.clamp), d_enc.data_ptr(), d_pred.data_ptr(), dW.data_ptr(), db.data_ptr(), ring_tiles,
+                lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                hidden.data_ptr() if ctx.have_hidden else None, dcost.data_ptr(), float(ctx.clamp), d_enc.data_ptr(), d_pred.data_ptr(), dW.data_ptr(), db.data_ptr(), ring_tiles,
                 ctx.flags, ws.data_ptr(), bwd_bytes, _stream_ptr(dev)), "joint_loss_bwd")
         if COLLECT_BACKWARD_STATS:
             global _last_backward_stats
             meta = ws[: (B + 5) * 4].view(torch.int32)     # tile table region starts at offset 0
             _last_backward_stats = torch.stack([meta[B + 4], meta[B]])
-        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None, None
 
 
 def _reduce(costs, reduction):
@@ -157,7 +168,7 @@ def _reduce(costs, reduction):
 def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths, blank: int = -1,
                     clamp: float = -1, reduction: str = "mean", validate: bool = True,
                     ring_bytes: Optional[int] = None, return_residuals: bool = False,
-                    skip_zero_tiles: bool = True):
+                    skip_zero_tiles: bool = True, save_hidden: Optional[bool] = None):
     """Fused replacement for `joint_ln(tanh(a.unsqueeze(2) + p.unsqueeze(1)))` (rnnt/joint.py:32-39) followed by
     `torchaudio.functional.rnnt_loss(..., blank, clamp, reduction)` (rnnt/model.py:35-41).
 
@@ -165,7 +176,9 @@ def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_length
     are joint_ln's parameters.  Per-utterance costs when reduction="none".  validate=True performs torchaudio's
     host-side length checks (one device sync, as the reference does); pass False on the hot loop.
     skip_zero_tiles=False makes the backward process every lattice tile, including those whose fp16 logit-gradients
-    are identically zero (same result, more work).
+    are identically zero (same result, more work).  save_hidden: keep the fp16 activations tanh(a+p) from the forward
+    for the backward (default; the reference's autograd keeps them in fp32) or recompute them there (False: the saved
+    state shrinks to 20 bytes per lattice cell).
     """
     _require_cuda(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths)
     if audio_frame.dtype != torch.float32 or text_frame.dtype != torch.float32:
@@ -180,7 +193,7 @@ def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_length
         _validate_lengths(audio_frame.shape[1], text_frame.shape[1], logit_lengths, target_lengths)
     costs, lp, lse, alpha, beta = _FusedJointLoss.apply(audio_frame, text_frame, weight.float(), bias.float(),
                                                         targets, logit_lengths, target_lengths, int(blank),
-                                                        float(clamp), ring_bytes, bool(skip_zero_tiles))
+                                                        float(clamp), ring_bytes, bool(skip_zero_tiles), save_hidden)
     out = _reduce(costs, reduction)
     if return_residuals:
         return out, dict(lp=lp, lse=lse, alpha=alpha, beta=beta)

@@ -27,8 +27,9 @@ def make_inputs(B, T, U, H, V, seed=1234, ragged=False, device="cuda", scale=1.0
     return dict(enc=to(enc), pred=to(pred), W=to(W), b=to(b), targets=to(targets), T_len=to(T_len), U_len=to(U_len))
 
 
-def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0):
-    """Call the C-ABI forward + backward directly; returns outputs plus the raw workspace and its layout."""
+def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0, save_hidden=True):
+    """Call the C-ABI forward + backward directly; returns outputs plus the raw workspace and its layout.
+    save_hidden=False exercises the memory-lean mode (per-SM scratch in the forward, recomputing backward)."""
     from rnnt_b200 import _lib
     from rnnt_b200.functional import _stream_ptr, pick_ring_tiles
     L = _lib.lib()
@@ -39,11 +40,14 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0):
     V = W.shape[0]
     dev = enc.device
     if ring_tiles is None:
-        ring_tiles = pick_ring_tiles(B, T, U1, H, V)
+        ring_tiles = pick_ring_tiles(B, T, U1, H, V, have_hidden=save_hidden)
     offs = (C.c_int64 * 8)()
     hp, vp = C.c_int(0), C.c_int(0)
-    _lib.check(L.rnnt_b200_debug_ws_layout(B, T, U1, H, V, ring_tiles, offs, C.byref(hp), C.byref(vp)), "layout")
+    _lib.check(L.rnnt_b200_debug_ws_layout(B, T, U1, H, V, ring_tiles, int(save_hidden), offs, C.byref(hp),
+                                           C.byref(vp)), "layout")
     ws = torch.zeros(int(offs[6]), dtype=torch.uint8, device=dev)
+    hidden = torch.zeros(L.rnnt_b200_hidden_bytes(B, T, U1, H), dtype=torch.uint8, device=dev) if save_hidden else None
+    hptr = hidden.data_ptr() if save_hidden else None
     f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
     out = dict(costs=f(B), lp=f(B, T, U1, 2), lse=f(B, T, U1), alpha=f(B, T, U1), beta=f(B, T, U1),
                d_enc=f(B, T, H), d_pred=f(B, U1, H), dW=f(V, H), db=f(V))
@@ -53,28 +57,32 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0):
         enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
         targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["costs"].data_ptr(),
         out["lp"].data_ptr(), out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(),
-        status.data_ptr(), ws.data_ptr(), ws.numel(), st), "fwd")
+        hptr, status.data_ptr(), ws.data_ptr(), ws.numel(), st), "fwd")
     torch.cuda.synchronize()
     if dcost is None:
         dcost = torch.ones(B, dtype=torch.float32, device=dev)
     _lib.check(L.rnnt_b200_joint_loss_bwd(
         enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
         targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["lp"].data_ptr(),
-        out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(), dcost.data_ptr(), float(clamp),
+        out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(), hptr, dcost.data_ptr(), float(clamp),
         out["d_enc"].data_ptr(), out["d_pred"].data_ptr(), out["dW"].data_ptr(), out["db"].data_ptr(),
         ring_tiles, flags, ws.data_ptr(), ws.numel(), st), "bwd")
     torch.cuda.synchronize()
     meta = ws[int(offs[0]): int(offs[0]) + (B + 5) * 4].view(torch.int32)
-    out.update(ws=ws, offs=[int(x) for x in offs], Hp=hp.value, Vp=vp.value, ring_tiles=ring_tiles,
+    out.update(ws=ws, hidden=hidden, offs=[int(x) for x in offs], Hp=hp.value, Vp=vp.value, ring_tiles=ring_tiles,
                status=int(status.item()), total_tiles=int(meta[B]), active_tiles=int(meta[B + 4]))
     return out
 
 
 def ring_views(out):
+    """g ring, activation rows (ring when recomputed; else the tile-indexed residual buffer), gradient scale S."""
     ws, offs, Hp, Vp = out["ws"], out["offs"], out["Hp"], out["Vp"]
     rows = out["ring_tiles"] * 128
     g = ws[offs[4]:offs[4] + rows * Vp * 2].view(torch.float16).view(rows, Vp)
-    h = ws[offs[5]:offs[5] + rows * Hp * 2].view(torch.float16).view(rows, Hp)
+    if out["hidden"] is not None:
+        h = out["hidden"].view(torch.float16).view(-1, Hp)
+    else:
+        h = ws[offs[5]:offs[5] + rows * Hp * 2].view(torch.float16).view(rows, Hp)
     B = out["costs"].numel()
     scale = ws[offs[0] + (B + 2) * 4: offs[0] + (B + 4) * 4].view(torch.float32)   # {S, 1/S}
     return g, h, float(scale[0])

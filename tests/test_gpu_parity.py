@@ -86,6 +86,48 @@ def test_multi_chunk_backward_equals_single_chunk():
         assert rel_err(many[k], one[k])[0] < 1e-5, k
 
 
+def test_recompute_mode_equals_saved_activation_mode():
+    """hidden = NULL: per-SM activation scratch in the forward, producers inside the backward kernel.  Same numbers."""
+    import rnnt_b200
+    for shape, kw in (((2, 40, 20, 256, 1024), {}), ((3, 50, 11, 72, 300), dict(ring_tiles=5)),
+                      ((2, 130, 30, 64, 256), {})):
+        inp = make_inputs(*shape, ragged=True, seed=11)
+        saved = fused_raw(inp, **kw)
+        lean = fused_raw(inp, save_hidden=False, **kw)
+        assert torch.equal(saved["costs"], lean["costs"])
+        assert torch.equal(saved["lp"], lean["lp"])
+        for k in ("d_enc", "d_pred", "dW", "db"):
+            assert rel_err(lean[k], saved[k])[0] < 2e-6, (shape, k, rel_err(lean[k], saved[k]))
+    # public API: loss-only evaluation (no grad -> no residual buffer) and the save_hidden switch
+    inp = make_inputs(2, 40, 20, 256, 1024, ragged=True, seed=11)
+    args = (inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"])
+    with torch.no_grad():
+        plain = rnnt_b200.joint_rnnt_loss(inp["enc"], *args, reduction="none")
+    grads = []
+    for save in (True, False):
+        enc = inp["enc"].clone().requires_grad_(True)
+        costs = rnnt_b200.joint_rnnt_loss(enc, *args, reduction="none", save_hidden=save)
+        assert torch.equal(costs.detach(), plain)
+        costs.sum().backward()
+        grads.append(enc.grad)
+    assert rel_err(grads[1], grads[0])[0] < 2e-6
+
+
+def test_saved_activations_are_the_fp16_tanh():
+    """The residual buffer holds h = tanh(enc+pred) in fp16, one 128-row block per 16(t) x 8(u) lattice tile."""
+    from helpers import tile_rows
+    inp = make_inputs(2, 21, 9, 64, 256, ragged=True, seed=5)
+    out = fused_raw(inp)
+    h = out["hidden"].view(torch.float16).view(-1, out["Hp"]).float()
+    rows = tile_rows(inp["T_len"].cpu(), inp["U_len"].cpu())
+    assert h.shape[0] >= len(rows)
+    want = torch.tanh(inp["enc"].unsqueeze(2) + inp["pred"].unsqueeze(1))
+    for r in range(0, len(rows), 7):
+        b, t, u, valid = rows[r]
+        if valid:
+            assert (h[r, :64] - want[b, t, u]).abs().max() < 2e-3
+
+
 def test_zero_tile_skipping_is_exact():
     """Tiles dropped from the backward hold only zeros in the fp16 gradient ring: results equal the all-tiles run."""
     inp = make_inputs(2, 160, 40, 128, 512, ragged=True, seed=17)
