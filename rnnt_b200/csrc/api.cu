@@ -129,13 +129,12 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
 
   const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
-  const int grid = static_cast<int>(std::min<int64_t>(rb::device_sm_count(), max_tiles));
   // activation rows h = tanh(enc+pred): the caller's residual buffer (one 128-row block per lattice tile) or a
   // small per-CTA scratch when no backward will follow
   __half* hbuf = hidden ? static_cast<__half*>(hidden) : reinterpret_cast<__half*>(ws + w.h_scratch);
   const uint64_t hrows = static_cast<uint64_t>(hidden ? max_tiles : w.scratch_tiles) * kTileM;
   CUtensorMap tmW, tmH;
-  rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
+  rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmH, hbuf, 2, w.Hp, hrows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
@@ -150,7 +149,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
   a.h_out = hbuf; a.h_map = hidden ? 0 : 2; a.g_ring = nullptr;
-  rc = rb::launch_joint_gemm(0, true, tmW, tmH, a, grid, stream);
+  rc = rb::launch_joint_gemm(0, true, tmW, tmH, a, max_tiles, stream);
   if (rc) return rc;
   return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
 }
@@ -204,8 +203,8 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
 
   const uint64_t h_rows = hidden ? static_cast<uint64_t>(max_tiles) * kTileM : ring_rows;
   CUtensorMap tmW, tmWmn, tmG256, tmHk, tmGmn, tmHmn;
-  // W [Vp, Hp]: K-major boxes (64 k x 256 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
-  rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 256);
+  // W [Vp, Hp]: K-major boxes (64 k x 128 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
+  rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmWmn, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
@@ -237,7 +236,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     a.h_out = h_src; a.h_map = h_map; a.g_ring = g_ring;
-    rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, a, grid, stream);
+    rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, a, chunk_tiles, stream);
     if (rc) return rc;
 
     rb::DhArgs d{};

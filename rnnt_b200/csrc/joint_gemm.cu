@@ -9,18 +9,22 @@
 // (fp16 operands: tanh output lies in [-1,1] and joint weights are O(1), so fp16's 11-bit mantissa gives 8x
 // finer rounding than bf16 at the same tensor-core rate; accumulation is fp32 in TMEM.)
 //
-// Structure (1 persistent CTA / SM, work unit = 16(t) x 8(u) lattice tile = 128 GEMM rows):
+// Structure (persistent CTA PAIRS, one CTA per SM; work unit per CTA = 16(t) x 8(u) lattice tile = 128 GEMM rows, the
+// two tiles of a pair form one M=256 tcgen05.mma.cta_group::2 issued by the pair's leader):
 //   * The hidden activations h = tanh(enc+pred) of a tile are produced ONCE, as fp16 rows of a global buffer
 //     (the residual the backward re-uses, or a small per-CTA scratch), by 8 producer warps that run one to two
 //     tiles AHEAD of the tensor pipe.  They are decoupled from the MMA pipeline: no shared-memory staging, no
 //     per-chunk hand-off, their MUFU/ALU work hides under the MMAs of the previous tile.
-//   * The GEMM itself is a plain TMA-fed tcgen05 pipeline: per (pass, k-chunk) one 256x64 W box and one 128x64 h box
-//     (just written, so an L2 hit) land in a 4-stage ring; a pass is one 256-column accumulator, and the two halves
+//   * The GEMM itself is a plain TMA-fed tcgen05 pipeline: per (pass, k-chunk) each CTA loads its own 128x64 h box
+//     (just written, so an L2 hit) and HALF of the 256x64 W box (the pair shares the B operand: 64 instead of 96 bytes
+//     of L2 traffic per SM and clock) into a 6-stage ring; a pass is one 256-column accumulator, and the two halves
 //     of TMEM ping-pong so that the epilogue of pass i overlaps the MMAs of pass i+1.
 //   * G mode with saved activations needs no producers at all.
 //
-// Warp roles: 0 TMA loader | 1 tcgen05.mma issuer | 2-9 epilogue (set e = warps 2+4e..5+4e drains accumulator e)
+// Warp roles: 0 TMA loader | 1 tcgen05.mma issuer (leader CTA only) | 2-9 epilogue (set e = warps 2+4e..5+4e drains accumulator e)
 //             | 10-17 (PRODUCE only) activation producers
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,9 +32,9 @@ namespace rb {
 
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kBytesA = kTileM * kBK * 2;  // 16 KB: 128 cells x 64 k
-constexpr int kBytesB = kBN * kBK * 2;     // 32 KB: 256 classes x 64 k
+constexpr int kStages = 6;
+constexpr int kBytesA = kTileM * kBK * 2;       // 16 KB: 128 cells x 64 k
+constexpr int kBytesB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's 128 of the pass's 256 classes x 64 k
 constexpr int kStageBytes = kBytesA + kBytesB;
 constexpr int kFirstEpiWarp = 2;
 constexpr int kNumEpiWarps = 8;
@@ -56,7 +60,7 @@ size_t joint_gemm_smem_bytes() { return SmemLayout::total + 1024; }
 int joint_gemm_scratch_tiles(int grid) { return grid * kScratchSlots; }
 
 template <int MODE, bool PRODUCE>  // MODE 0 = forward (lse + gather), 1 = backward (gradient ring)
-__global__ void __launch_bounds__(PRODUCE ? kThreadsProd : kThreadsNoProd, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PRODUCE ? kThreadsProd : kThreadsNoProd, 1)
 joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, JointArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -73,6 +77,8 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair (issues the MMAs)
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
   const int total_tiles = p.n_active ? __ldg(p.n_active) : __ldg(p.tile_off + p.B);
   const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots [tile_begin, tile_end)
@@ -90,33 +96,41 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmH);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + 8 * s, 1);
+      mbar_init(full + 8 * s, 2);        // leader's copy: one expect_tx arrival per CTA of the pair
       mbar_init(empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full + 8 * a, 1);
-      mbar_init(tmem_empty + 8 * a, kNumEpiWarps / 2);
+      mbar_init(tmem_empty + 8 * a, kNumEpiWarps);   // leader's copy: 4 warps of set a in each CTA
       mbar_init(h_ready + 8 * a, kNumProdWarps);
       mbar_init(tile_done + 8 * a, 1);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();      // barrier inits and TMEM allocation of both CTAs are visible before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+// this CTA's tiles: slot = base + rank for base = tile_begin + 2 * (pair + i * npairs); a pair whose second slot is past
+// the end still runs (the leader's MMA spans both CTAs) with that CTA's outputs suppressed
+#define RB_TILE_LOOP(cntvar)                                                                                    \
+  for (int base_ = p.tile_begin + 2 * pair; base_ < tile_end; base_ += 2 * npairs, ++cntvar)
 
   if (warp == 0) {
     // ===================================================================== TMA loader (W boxes + activation boxes)
     if (lane == 0) {
       uint32_t it = 0, cnt = 0;
-      for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++cnt) {
-        const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
-        const int row0 = h_row0(slot, tile, cnt);
+      RB_TILE_LOOP(cnt) {
+        const int slot = base_ + rank;
+        const bool mine = slot < tile_end;
+        const int tile = !mine ? 0 : (p.tile_list ? __ldg(p.tile_list + slot) : slot);
+        const int row0 = mine ? h_row0(slot, tile, cnt) : 0;   // no tile: any resident row block (results unused)
         if (PRODUCE) {
           mbar_wait(h_ready + 8 * (cnt & 1), (cnt >> 1) & 1);
           fence_proxy_async_all();   // the producers' generic-proxy global stores -> TMA (async proxy) reads
@@ -125,18 +139,20 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           for (int kc = 0; kc < nk; ++kc, ++it) {
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(empty + 8 * s, ph ^ 1);
-            mbar_expect_tx(full + 8 * s, kStageBytes);
-            tma_load_2d(ring + s * kStageBytes, &tmW, full + 8 * s, kc * kBK, pass * kBN);
-            tma_load_2d(ring + s * kStageBytes + kBytesB, &tmH, full + 8 * s, kc * kBK, row0);
+            const uint32_t full_leader = mapa_shared(full + 8 * s, 0);
+            if (rank == 0) mbar_expect_tx(full + 8 * s, 2 * kStageBytes);   // both CTAs' boxes land on the leader's barrier
+            else mbar_arrive_cluster(full_leader);
+            tma_load_2d_pair(ring + s * kStageBytes, &tmW, full_leader, kc * kBK, pass * kBN + rank * (kBN / 2));
+            tma_load_2d_pair(ring + s * kStageBytes + kBytesB, &tmH, full_leader, kc * kBK, row0);
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    constexpr uint32_t idesc = make_idesc(kTileM, kBN, 0, 0, kFmtF16, kFmtF16);
+  } else if (warp == 1 && rank == 0) {
+    // ===================================================================== MMA issuer (leader CTA of the pair)
+    constexpr uint32_t idesc = make_idesc(2 * kTileM, kBN, 0, 0, kFmtF16, kFmtF16);
     uint32_t it = 0, pc = 0, cnt = 0;
-    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++cnt) {
+    RB_TILE_LOOP(cnt) {
       for (int pass = 0; pass < npass; ++pass, ++pc) {
         const uint32_t acc = pc & 1;
         mbar_wait(tmem_empty + 8 * acc, ((pc >> 1) & 1) ^ 1);
@@ -151,17 +167,17 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
               const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_f16(tmem_base + acc * kBN, ad, bd, idesc, (kc | k) != 0);
+              umma_f16_pair(tmem_base + acc * kBN, ad, bd, idesc, (kc | k) != 0);
             }
-            umma_commit(empty + 8 * s);
+            umma_commit_pair(empty + 8 * s, 3);
           }
           __syncwarp();
         }
-        if (lane == 0) umma_commit(tmem_full + 8 * acc);
+        if (lane == 0) umma_commit_pair(tmem_full + 8 * acc, 3);
         __syncwarp();
       }
       if (PRODUCE) {
-        if (lane == 0) umma_commit(tile_done + 8 * (cnt & 1));   // this tile's activation rows are consumed
+        if (lane == 0) umma_commit_pair(tile_done + 8 * (cnt & 1), 3);   // both tiles' activation rows are consumed
         __syncwarp();
       }
     }
@@ -173,12 +189,15 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int row = lane_grp * 32 + lane;
     const int ti = row >> 3, ui = row & 7;
     float4* xchg = reinterpret_cast<float4*>(smem_gen + SL::xchg);
+    const uint32_t tmem_empty_leader = mapa_shared(tmem_empty + 8 * eset, 0);
     uint32_t pc = 0, tcount = 0;
-    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++tcount) {
-      const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
+    RB_TILE_LOOP(tcount) {
+      const int slot = base_ + rank;
+      const bool mine = slot < tile_end;
+      const int tile = !mine ? 0 : (p.tile_list ? __ldg(p.tile_list + slot) : slot);
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
       const int t = tc.t0 + ti, u = tc.u0 + ui;
-      const bool valid = (t < tc.Tb) && (u <= tc.Ub);
+      const bool valid = mine && (t < tc.Tb) && (u <= tc.Ub);
       const long long cell = (static_cast<long long>(tc.b) * p.T + min(t, p.T - 1)) * p.U1 + min(u, p.U1 - 1);
       int tgt = -1;
       if (valid && u < tc.Ub) tgt = __ldg(p.targets + static_cast<long long>(tc.b) * p.tgt_ld + u);
@@ -199,7 +218,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (static_cast<int>(pc & 1) != eset) continue;
         mbar_wait(tmem_full + 8 * eset, (pc >> 1) & 1);
         tc_fence_after();
-        const int nchunk = (p.dbg & 1) ? 0 : (kBN / 32);
+        const int nchunk = ((p.dbg & 1) || !mine) ? 0 : (kBN / 32);
         for (int c32 = 0; c32 < nchunk; ++c32) {
           const int col0 = pass * kBN + c32 * 32;  // global column of v[0]
           float v[32];
@@ -263,7 +282,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + 8 * eset);
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
       }
       if (MODE == 0) {
         // combine the two sets' online-softmax partials: set 1 -> smem -> set 0 writes lp / lse
@@ -291,7 +310,14 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int rg = warp - kFirstProdWarp;
     const int c = lane & 7, rs = lane >> 3;
     uint32_t cnt = 0;
-    for (int slot = p.tile_begin + blockIdx.x; slot < tile_end; slot += gridDim.x, ++cnt) {
+    RB_TILE_LOOP(cnt) {
+      const int slot = base_ + rank;
+      if (slot >= tile_end) {            // the pair's odd tile out: nothing to produce, keep the barrier protocol
+        if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready + 8 * (cnt & 1));
+        continue;
+      }
       const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
       const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
       const int row0 = h_row0(slot, tile, cnt);
@@ -326,24 +352,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
       __half* out_base = p.h_out + static_cast<long long>(row0 + rg * 16) * p.Hp + 8 * c;
       for (int kc = 0; kc < nk; ++kc) {
+        if (p.dbg & 2) break;   // diagnostics: leave the buffer's previous contents (valid data from an earlier call)
         uint4 w[2][2];
-        if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {        // t-row
+        for (int i = 0; i < 2; ++i) {        // t-row
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {      // u = rs + 4j
-              const float4 a0 = e_cur[i][0], a1 = e_cur[i][1], b0 = p_cur[j][0], b1 = p_cur[j][1];
-              w[i][j].x = pack_f16x2(tanh_approx(a0.x + b0.x), tanh_approx(a0.y + b0.y));
-              w[i][j].y = pack_f16x2(tanh_approx(a0.z + b0.z), tanh_approx(a0.w + b0.w));
-              w[i][j].z = pack_f16x2(tanh_approx(a1.x + b1.x), tanh_approx(a1.y + b1.y));
-              w[i][j].w = pack_f16x2(tanh_approx(a1.z + b1.z), tanh_approx(a1.w + b1.w));
-            }
+          for (int j = 0; j < 2; ++j) {      // u = rs + 4j
+            const float4 a0 = e_cur[i][0], a1 = e_cur[i][1], b0 = p_cur[j][0], b1 = p_cur[j][1];
+            w[i][j].x = pack_f16x2(tanh_approx(a0.x + b0.x), tanh_approx(a0.y + b0.y));
+            w[i][j].y = pack_f16x2(tanh_approx(a0.z + b0.z), tanh_approx(a0.w + b0.w));
+            w[i][j].z = pack_f16x2(tanh_approx(a1.x + b1.x), tanh_approx(a1.y + b1.y));
+            w[i][j].w = pack_f16x2(tanh_approx(a1.z + b1.z), tanh_approx(a1.w + b1.w));
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) w[i][j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
         }
         // the inputs of the next chunk are requested before the stores of this one are issued
         if (kc + 1 < nk) load_chunk(kc + 1, e_cur, p_cur);
@@ -359,22 +379,52 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   }
 
+#undef RB_TILE_LOOP
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();      // the peer may still be signalling this CTA's barriers / reading its shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
+// CTA pairs that can be co-resident (one CTA per SM, both SMs of a pair in one TPC); cached per device and variant.
+template <int MODE, bool PRODUCE>
+static int max_pairs(size_t smem) {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return device_sm_count() / 2;
+  if (cached[dev] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (device_sm_count() / 2));
+    cfg.blockDim = dim3(PRODUCE ? kThreadsProd : kThreadsNoProd);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, joint_gemm_kernel<MODE, PRODUCE>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = device_sm_count() / 2;
+    }
+    cached[dev] = std::min(n, device_sm_count() / 2);
+  }
+  return cached[dev];
+}
+
 int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
-                      int grid, cudaStream_t stream) {
+                      long long max_tiles, cudaStream_t stream) {
   ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
   const size_t smem = SmemLayout::total + 1024;
+  const long long want_pairs = std::max<long long>(1, (max_tiles + 1) / 2);
 #define RB_LAUNCH_JG(M, P)                                                                                         \
   do {                                                                                                             \
     RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                        (int)smem));                                                                \
+    const int grid = 2 * static_cast<int>(std::min<long long>(max_pairs<M, P>(smem), want_pairs));                 \
+    if (args.dbg & 8) fprintf(stderr, "rnnt_b200: joint gemm mode %d produce %d grid %d\n", M, (int)P, grid);       \
     joint_gemm_kernel<M, P><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, args);            \
   } while (0)
   if (mode == 0) {

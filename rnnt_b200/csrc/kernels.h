@@ -93,8 +93,9 @@ int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream);
 
 size_t joint_gemm_smem_bytes();
 int joint_gemm_scratch_tiles(int grid);   // tiles of per-CTA activation scratch the forward needs when h_map == 2
+// tmW: 64(k) x 128(v) boxes (each CTA of a pair loads half of a 256-class block); max_tiles bounds the work list
 int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
-                      int grid, cudaStream_t stream);
+                      long long max_tiles, cudaStream_t stream);
 int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, int grid,
                    cudaStream_t stream);
 int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream);

@@ -14,8 +14,11 @@ def step():
     l = joint_rnnt_loss(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"], validate=False)
     if mode == "fwdbwd":
         l.backward()
+# warm up (and fill the activation buffer) with the full kernels, then switch the diagnostic stub bits on
+dbg = os.environ.pop("RNNT_B200_DBG", "0")
 for _ in range(3): step()
 torch.cuda.synchronize()
+os.environ["RNNT_B200_DBG"] = dbg
 lines = []
 proc = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
 th = threading.Thread(target=lambda: [lines.append(l) for l in proc.stdout], daemon=True); th.start()
