@@ -202,30 +202,27 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
 
   const uint64_t h_rows = hidden ? static_cast<uint64_t>(max_tiles) * kTileM : ring_rows;
-  CUtensorMap tmW, tmWmn, tmG256, tmHk, tmGmn, tmHmn;
+  CUtensorMap tmW, tmWmn, tmG128, tmHk, tmGmn, tmHmn;
   // W [Vp, Hp]: K-major boxes (64 k x 128 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
   rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmWmn, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
   // activations: 64 x 128 K-major boxes for the logit recompute, 64 x 64 boxes for the MN-major dW operand;
-  // gradient ring: 64 x 256 K-major boxes for dh, 64 x 64 boxes for the MN-major dW operand
+  // gradient ring: 64 x 128 K-major boxes for dh (one lattice tile per CTA of a pair), 64 x 64 boxes for the MN-major dW operand
   rc = rb::make_tmap_2d(&tmHk, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
-  rc = rb::make_tmap_2d(&tmG256, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 256);
+  rc = rb::make_tmap_2d(&tmG128, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmGmn, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 64);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmHmn, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
 
-  const int sms = rb::device_sm_count();
   const int64_t nchunks = (max_tiles + ring_tiles - 1) / ring_tiles;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int tile_begin = static_cast<int>(c * ring_tiles);
     const int64_t chunk_tiles = std::min<int64_t>(ring_tiles, max_tiles - c * ring_tiles);
-    const int grid = static_cast<int>(std::min<int64_t>(sms, chunk_tiles));
-
     rb::JointArgs a{};
     a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st;
     a.pred = pred; a.pred_sb = static_cast<long long>(U1) * H; a.pred_su = H;
@@ -246,17 +243,13 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     d.B = B; d.T = T; d.U1 = U1; d.H = H; d.Hp = w.Hp; d.Vp = w.Vp;
     d.tile_begin = tile_begin; d.tile_cap = static_cast<int>(ring_tiles);
     d.d_enc = d_enc; d.d_pred = d_pred;
-    const int64_t dh_items = ((chunk_tiles + 1) / 2) * ((w.Hp + 127) / 128);
-    rc = rb::launch_dh_gemm(tmG256, tmWmn, d, static_cast<int>(std::min<int64_t>(sms, dh_items)), stream);
+    rc = rb::launch_dh_gemm(tmG128, tmWmn, d, chunk_tiles, stream);
     if (rc) return rc;
 
     rb::DwArgs g{};
     g.n_active = n_active; g.tile_list = tile_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
     g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW; g.db = dbias; g.gscale = gscale;
-    const int out_tiles = (w.Vp / kTileM) * ((((w.Hp + 255) / 256) + 1) / 2);
-    const int64_t kchunks = chunk_tiles * 2;
-    g.ksplit = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(sms / std::max(1, out_tiles), kchunks)));
-    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, stream);
+    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_tiles, stream);
     if (rc) return rc;
   }
   return 0;

@@ -9,17 +9,21 @@
 // values per thread (MUFU is otherwise idle here), and the fp32 atomics are coalesced over k.
 //   A operand: W^T block (128 k x 64 v) = MN-major view of the fp16 W[Vp,Hp] buffer (TMA, two 64x64 boxes)
 //   B operand: gradient ring g [ring_rows, Vp] fp16, K-major (TMA, one 64 x 256 box = two lattice tiles)
-// Work item = (pair of lattice tiles, block of 128 hidden units); accumulators ping-pong between the two halves of
-// TMEM so the epilogue of item i overlaps the MMAs of item i+1.
+// Work item of a CTA PAIR = (two lattice tiles = 256 cells, block of 256 hidden units): one tcgen05.mma.cta_group::2
+// with M = 256; each CTA stages its own 128 hidden units of W^T and HALF of the gradient box (one lattice tile), so
+// the L2 -> shared-memory traffic is 64 instead of 96 bytes per SM and clock.  Accumulators ping-pong between the two
+// halves of TMEM so the epilogue of item i overlaps the MMAs of item i+1.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace rb {
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kBytesA = kBK * 128 * 2;      // 16 KB: 64 v x 128 k
-constexpr int kBytesB = kBN * kBK * 2;      // 32 KB: 256 cells x 64 v
+constexpr int kStages = 6;
+constexpr int kBytesA = kBK * 128 * 2;          // 16 KB: 64 v x 128 k (this CTA's hidden units)
+constexpr int kBytesB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's 128 of the item's 256 cells x 64 v
 constexpr int kNumThreads = 192;
 constexpr int kTmemCols = 512;
 
@@ -30,7 +34,7 @@ struct SmemLayout {
   static constexpr int total = bars + 256;
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmWmn, DhArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -43,46 +47,53 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int total_tiles = __ldg(p.n_active);
   const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots
   const int ntiles = max(0, tile_end - p.tile_begin);
   const int ncb = (ntiles + 1) / 2;                 // cell blocks of 2 lattice tiles (256 ring rows)
-  const int nhb = (p.Hp + 127) / 128;               // hidden blocks of 128
+  const int nhb = (p.Hp + 255) / 256;               // hidden blocks of 256 (128 per CTA of the pair)
   const int nitems = ncb * nhb;
   const int nk = p.Vp / kBK;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmG);
     tma_prefetch_desc(&tmWmn);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 4); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full + 8 * s, 2); mbar_init(empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 8); }
     mbar_fence_init();
   }
-  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int item = pair; item < nitems; item += npairs) {
         const int cb = item / nhb, hb = item % nhb;
+        const int k0 = hb * 256 + rank * 128;            // this CTA's hidden units
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(full + 8 * s, kBytesA + kBytesB);
-          tma_load_2d(a_ring + s * kBytesA, &tmWmn, full + 8 * s, hb * 128, kc * kBK);
-          tma_load_2d(a_ring + s * kBytesA + 8192, &tmWmn, full + 8 * s, hb * 128 + 64, kc * kBK);
-          tma_load_2d(b_ring + s * kBytesB, &tmG, full + 8 * s, kc * kBK, cb * 256);
+          const uint32_t full_leader = mapa_shared(full + 8 * s, 0);
+          if (rank == 0) mbar_expect_tx(full + 8 * s, 2 * (kBytesA + kBytesB));
+          else mbar_arrive_cluster(full_leader);
+          tma_load_2d_pair(a_ring + s * kBytesA, &tmWmn, full_leader, k0, kc * kBK);
+          tma_load_2d_pair(a_ring + s * kBytesA + 8192, &tmWmn, full_leader, k0 + 64, kc * kBK);
+          tma_load_2d_pair(b_ring + s * kBytesB, &tmG, full_leader, kc * kBK, cb * 256 + rank * 128);
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(128, kBN, 1, 0, kFmtF16, kFmtF16);
+   if (rank == 0) {
+    constexpr uint32_t idesc = make_idesc(256, kBN, 1, 0, kFmtF16, kFmtF16);
     uint32_t it = 0, ic = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
+    for (int item = pair; item < nitems; item += npairs, ++ic) {
       const uint32_t acc = ic & 1, accph = (ic >> 1) & 1;
       mbar_wait(tmem_empty + 8 * acc, accph ^ 1);
       tc_fence_after();
@@ -96,23 +107,24 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);   // MN-major (W^T)
             const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);       // K-major (g)
-            umma_f16(tmem_base + acc * kBN, ad, bd, idesc, (kc | k) != 0);
+            umma_f16_pair(tmem_base + acc * kBN, ad, bd, idesc, (kc | k) != 0);
           }
-          umma_commit(empty + 8 * s);
+          umma_commit_pair(empty + 8 * s, 3);
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(tmem_full + 8 * acc);
+      if (lane == 0) umma_commit_pair(tmem_full + 8 * acc, 3);
       __syncwarp();
     }
+   }
   } else {
     const int lane_grp = warp & 3;
     const int krow = lane_grp * 32 + lane;      // hidden unit within the block = TMEM lane
     const float inv_s = __ldg(p.gscale + 1);
     uint32_t ic = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ic) {
+    for (int item = pair; item < nitems; item += npairs, ++ic) {
       const int cb = item / nhb, hb = item % nhb;
-      const int k = hb * 128 + krow;
+      const int k = hb * 256 + rank * 128 + krow;
       const bool k_ok = k < p.H;
       const int kk = k_ok ? k : 0;
       const uint32_t acc = ic & 1, accph = (ic >> 1) & 1;
@@ -163,22 +175,26 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tmem_empty + 8 * acc, 0));
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, kTmemCols); }
 }
 
 }  // namespace
 
-int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, int grid,
+int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, long long chunk_tiles,
                    cudaStream_t stream) {
   ProfScope prof_(kProfDh, stream);
   const size_t smem = SmemLayout::total + 1024;
   RB_CUDA_CHECK(cudaFuncSetAttribute(dh_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long items = ((chunk_tiles + 1) / 2) * ((args.Hp + 255) / 256);
+  const int pairs = max_cta_pairs(reinterpret_cast<const void*>(dh_gemm_kernel), kNumThreads, smem);
+  const int grid = 2 * static_cast<int>(std::max<long long>(1, std::min<long long>(pairs, items)));
   dh_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmG, tmWmn, args);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;

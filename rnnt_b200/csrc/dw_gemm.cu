@@ -3,9 +3,13 @@
 // Replaces the weight-gradient GEMM of joint_ln's autograd backward (rnnt/joint.py:39).
 // Both operands are read as MN-major views of the row-major rings written by the G-mode joint kernel:
 //   A[m=v][k=c] = g_ring[c][v]      B[n=kh][k=c] = h_ring[c][kh]
-// One CTA owns a 128(v) x 512(k_h) block of dW (two TMEM accumulators = all 512 columns) for one K split and
-// adds it into the fp32 dW with vector reductions (red.global.add.v4.f32).  The CTAs of the first k_h block also
-// produce db: while the MMAs run, their (otherwise idle) epilogue warps sum every A stage over its 64 cells.
+// A CTA PAIR owns a 256(v) x 512(k_h) block of dW for one K split (tcgen05.mma.cta_group::2, M = 256: each CTA holds
+// its 128 classes x 512 hidden units as two TMEM accumulators = all 512 columns, stages its own 128 classes of g^T and
+// HALF of each activation box -> 48 instead of 80 bytes of L2 traffic per SM and clock) and adds it into the fp32 dW
+// with vector reductions (red.global.add.v4.f32).  The CTAs of the first k_h block also produce db: while the MMAs
+// run, their (otherwise idle) epilogue warps sum every A stage over its 64 cells.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -13,9 +17,9 @@ namespace rb {
 namespace {
 
 constexpr int kStagesA = 4;
-constexpr int kStagesB = 4;
-constexpr int kBytesA = kBK * kTileM * 2;   // 16 KB: 64 cells x 128 v  (two 64x64 boxes)
-constexpr int kBytesB = kBK * kBN * 2;      // 32 KB: 64 cells x 256 kh (four 64x64 boxes)
+constexpr int kStagesB = 8;
+constexpr int kBytesA = kBK * kTileM * 2;       // 16 KB: 64 cells x 128 v  (two 64x64 boxes; this CTA's classes)
+constexpr int kBytesB = kBK * (kBN / 2) * 2;    // 16 KB: 64 cells x 128 kh (two 64x64 boxes; this CTA's half of N=256)
 constexpr int kNumThreads = 192;
 constexpr int kTmemCols = 512;
 
@@ -26,7 +30,7 @@ struct SmemLayout {
   static constexpr int total = bars + 256;
 };
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant__ CUtensorMap tmHmn, DwArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -37,37 +41,46 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
   const uint32_t b_full = bars, b_empty = bars + 8 * kStagesB;
   const uint32_t a_full = bars + 16 * kStagesB, a_empty = a_full + 8 * kStagesA;
   const uint32_t tmem_full = a_empty + 8 * kStagesA;
+  const uint32_t a_peer = tmem_full + 8;    // leader only: the peer CTA's A stage has landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + SmemLayout::bars + 200);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
   const int total_tiles = __ldg(p.n_active);
   const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
   const int nkc = max(0, tile_end - p.tile_begin) * (kTileM / kBK);   // 64-row K chunks in this ring chunk
 
   const int nblk_total = (p.Hp + kBN - 1) / kBN;
   const int nht = (nblk_total + 1) / 2;
-  const int nvt = p.Vp / kTileM;
-  int bid = blockIdx.x;
+  const int nvt = p.Vp / (2 * kTileM);
+  int bid = blockIdx.x >> 1;          // pair index
   const int vt = bid % nvt; bid /= nvt;
   const int ht = bid % nht; bid /= nht;
   const int ks = bid;
   const int nblk = min(2, nblk_total - ht * 2);
   const int k_begin = static_cast<int>(static_cast<long long>(nkc) * ks / p.ksplit);
   const int k_end = static_cast<int>(static_cast<long long>(nkc) * (ks + 1) / p.ksplit);
-  if (k_begin >= k_end) return;   // uniform over the CTA
+  if (k_begin >= k_end) return;   // uniform over the pair
   const bool do_db = (ht == 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmGmn);
     tma_prefetch_desc(&tmHmn);
-    for (int s = 0; s < kStagesB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    for (int s = 0; s < kStagesA; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, do_db ? 5 : 1); }
+    // b_full: the leader's copy collects both CTAs' boxes (one arrival per CTA).  a_full stays local (the db reducers of
+    // each CTA read their own A stage); the peer's MMA warp forwards "my A stage landed" to the leader's a_peer.
+    for (int s = 0; s < kStagesB; ++s) { mbar_init(b_full + 8 * s, 2); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < kStagesA; ++s) {
+      mbar_init(a_full + 8 * s, 1);
+      mbar_init(a_empty + 8 * s, do_db ? 5 : 1);
+      mbar_init(a_peer + 8 * s, 1);
+    }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), kTmemCols); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -80,7 +93,8 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
         mbar_expect_tx(a_full + 8 * sa, kBytesA);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          tma_load_2d(a_ring + sa * kBytesA + j * 8192, &tmGmn, a_full + 8 * sa, vt * kTileM + j * 64, kc * kBK);
+          tma_load_2d(a_ring + sa * kBytesA + j * 8192, &tmGmn, a_full + 8 * sa,
+                      (vt * 2 + rank) * kTileM + j * 64, kc * kBK);
         // activation rows of this 64-cell chunk: ring rows, or the forward's residual buffer (tile-indexed)
         const int hrow = (p.h_map == 0)
                              ? __ldg(p.tile_list + p.tile_begin + (kc >> 1)) * kTileM + (kc & 1) * kBK
@@ -88,20 +102,33 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
         for (int blk = 0; blk < nblk; ++blk, ++itb) {
           const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
           mbar_wait(b_empty + 8 * sb, phb ^ 1);
-          mbar_expect_tx(b_full + 8 * sb, kBytesB);
+          const uint32_t full_leader = mapa_shared(b_full + 8 * sb, 0);
+          if (rank == 0) mbar_expect_tx(b_full + 8 * sb, 2 * kBytesB);
+          else mbar_arrive_cluster(full_leader);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            tma_load_2d(b_ring + sb * kBytesB + j * 8192, &tmHmn, b_full + 8 * sb,
-                        (ht * 2 + blk) * kBN + j * 64, hrow);
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d_pair(b_ring + sb * kBytesB + j * 8192, &tmHmn, full_leader,
+                             (ht * 2 + blk) * kBN + rank * (kBN / 2) + j * 64, hrow);
         }
       }
     }
+  } else if (warp == 1 && rank != 0) {
+    // peer CTA: tell the leader when this CTA's A stage is in shared memory
+    const uint32_t peer0 = mapa_shared(a_peer, 0);
+    uint32_t ita = 0;
+    for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
+      const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
+      mbar_wait(a_full + 8 * sa, pha);
+      if (lane == 0) mbar_arrive_cluster(peer0 + 8 * sa);
+      __syncwarp();
+    }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(kTileM, kBN, 1, 1, kFmtF16, kFmtF16);
+    constexpr uint32_t idesc = make_idesc(2 * kTileM, kBN, 1, 1, kFmtF16, kFmtF16);
     uint32_t ita = 0, itb = 0;
     for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
       const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
       mbar_wait(a_full + 8 * sa, pha);
+      mbar_wait(a_peer + 8 * sa, pha);
       for (int blk = 0; blk < nblk; ++blk, ++itb) {
         const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
         mbar_wait(b_full + 8 * sb, phb);
@@ -112,21 +139,21 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);   // MN-major
             const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);   // MN-major
-            umma_f16(tmem_base + blk * kBN, ad, bd, idesc, (kc > k_begin) || (k != 0));
+            umma_f16_pair(tmem_base + blk * kBN, ad, bd, idesc, (kc > k_begin) || (k != 0));
           }
-          umma_commit(b_empty + 8 * sb);
+          umma_commit_pair(b_empty + 8 * sb, 3);
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(a_empty + 8 * sa);
+      if (lane == 0) umma_commit_pair(a_empty + 8 * sa, 3);
       __syncwarp();
     }
-    if (lane == 0) umma_commit(tmem_full);
+    if (lane == 0) umma_commit_pair(tmem_full, 3);
     __syncwarp();
   } else {
     const int lane_grp = warp & 3;
     const int row = lane_grp * 32 + lane;
-    const int v = vt * kTileM + row;
+    const int v = (vt * 2 + rank) * kTileM + row;
     const float inv_s = __ldg(p.gscale + 1);
     if (do_db) {
       // column sums of g over the cells of every A stage (MN-major: 64 cell rows of 128 bytes per 64-v box)
@@ -180,17 +207,24 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+  cluster_sync_all();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, kTmemCols); }
 }
 
 }  // namespace
 
-int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream) {
+int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args_in, long long chunk_tiles,
+                   cudaStream_t stream) {
   ProfScope prof_(kProfDw, stream);
   const size_t smem = SmemLayout::total + 1024;
   RB_CUDA_CHECK(cudaFuncSetAttribute(dw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DwArgs args = args_in;
   const int nblk_total = (args.Hp + kBN - 1) / kBN;
-  const int grid = (args.Vp / kTileM) * ((nblk_total + 1) / 2) * args.ksplit;
+  const int out_blocks = (args.Vp / (2 * kTileM)) * ((nblk_total + 1) / 2);   // 256 x 512 blocks of dW, one pair each
+  const int pairs = max_cta_pairs(reinterpret_cast<const void*>(dw_gemm_kernel), kNumThreads, smem);
+  const long long kchunks = chunk_tiles * (kTileM / kBK);
+  args.ksplit = static_cast<int>(std::max<long long>(1, std::min<long long>(pairs / std::max(1, out_blocks), kchunks)));
+  const int grid = 2 * out_blocks * args.ksplit;
   dw_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmGmn, tmHmn, args);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;

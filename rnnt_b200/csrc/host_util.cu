@@ -68,6 +68,38 @@ int device_sm_count() {
   return cached[dev];
 }
 
+int max_cta_pairs(const void* kernel, int threads, size_t smem) {
+  // keyed on (device, kernel); a handful of kernels -> linear scan
+  struct Entry { int dev; const void* fn; int pairs; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  int dev = 0;
+  const int fallback = device_sm_count() / 2;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fallback;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Entry& e : cache)
+      if (e.dev == dev && e.fn == kernel) return e.pairs;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * fallback);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = fallback;
+  }
+  n = n < fallback ? n : fallback;
+  std::lock_guard<std::mutex> lk(mu);
+  cache.push_back({dev, kernel, n});
+  return n;
+}
+
 namespace {
 struct ProfRec { int family; cudaEvent_t start, end; };
 std::mutex g_prof_mu;

@@ -150,7 +150,9 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   } else if (warp == 1 && rank == 0) {
     // ===================================================================== MMA issuer (leader CTA of the pair)
-    constexpr uint32_t idesc = make_idesc(2 * kTileM, kBN, 0, 0, kFmtF16, kFmtF16);
+    // (diagnostics: dbg bit 16 reinterprets the operands as bf16 -- wrong numbers, used to measure operand-format power)
+    const uint32_t idesc = (p.dbg & 16) ? make_idesc(2 * kTileM, kBN, 0, 0, kFmtBF16, kFmtBF16)
+                                        : make_idesc(2 * kTileM, kBN, 0, 0, kFmtF16, kFmtF16);
     uint32_t it = 0, pc = 0, cnt = 0;
     RB_TILE_LOOP(cnt) {
       for (int pass = 0; pass < npass; ++pass, ++pc) {
@@ -389,31 +391,6 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   }
 }
 
-// CTA pairs that can be co-resident (one CTA per SM, both SMs of a pair in one TPC); cached per device and variant.
-template <int MODE, bool PRODUCE>
-static int max_pairs(size_t smem) {
-  static int cached[64] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return device_sm_count() / 2;
-  if (cached[dev] == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (device_sm_count() / 2));
-    cfg.blockDim = dim3(PRODUCE ? kThreadsProd : kThreadsNoProd);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, joint_gemm_kernel<MODE, PRODUCE>, &cfg) != cudaSuccess || n <= 0) {
-      cudaGetLastError();
-      n = device_sm_count() / 2;
-    }
-    cached[dev] = std::min(n, device_sm_count() / 2);
-  }
-  return cached[dev];
-}
-
 int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
                       long long max_tiles, cudaStream_t stream) {
   ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
@@ -423,7 +400,7 @@ int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUte
   do {                                                                                                             \
     RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                        (int)smem));                                                                \
-    const int grid = 2 * static_cast<int>(std::min<long long>(max_pairs<M, P>(smem), want_pairs));                 \
+    const int grid = 2 * static_cast<int>(std::min<long long>(max_cta_pairs(reinterpret_cast<const void*>(joint_gemm_kernel<M, P>), P ? kThreadsProd : kThreadsNoProd, smem), want_pairs));                 \
     if (args.dbg & 8) fprintf(stderr, "rnnt_b200: joint gemm mode %d produce %d grid %d\n", M, (int)P, grid);       \
     joint_gemm_kernel<M, P><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, args);            \
   } while (0)

@@ -96,9 +96,11 @@ int joint_gemm_scratch_tiles(int grid);   // tiles of per-CTA activation scratch
 // tmW: 64(k) x 128(v) boxes (each CTA of a pair loads half of a 256-class block); max_tiles bounds the work list
 int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
                       long long max_tiles, cudaStream_t stream);
-int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, int grid,
+// tmG: 64(v) x 128(cell) boxes of the gradient ring; chunk_tiles bounds the work-list slots of this ring chunk
+int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, long long chunk_tiles,
                    cudaStream_t stream);
-int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, cudaStream_t stream);
+int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, long long chunk_tiles,
+                   cudaStream_t stream);   // picks args.ksplit itself
 
 // prep / small kernels (prep.cu, lattice.cu, decode.cu)
 int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
