@@ -405,7 +405,7 @@ def run_gpu_arm(args):
         launches_dom = gemms[dom]["launches_per_step"]
         achieved = gemms[dom]["tflops"]
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
         if os.path.exists(tpath):     # DRAM bytes per launch of that kernel from the committed ncu --set full capture
             with open(tpath) as f:
                 traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
@@ -429,7 +429,8 @@ def run_gpu_arm(args):
                                          f"(BASELINE configs[1]); global batch {B * world}",
                                 parallelism=f"dp{world} by utterance, all-reduce of {V * H + V + PRED_GRAD_ELEMS} "
                                             "fp32 grads" if world > 1 else "single GPU",
-                                l2="3 rotating input sets (210 MB > 126 MB L2) + multi-GB/step ring traffic",
+                                l2="3 rotating input sets (210 MB > 126 MB L2); every step also streams the 2.7 GB "
+                                   "activation residual and the gradient ring through HBM",
                                 operands="fp16 x fp16 -> fp32 (TMEM), fp32 elsewhere",
                                 backward_tiles=dict(active=active_tiles, total=total_tiles, fraction=bwd_frac,
                                                     note="lattice tiles whose fp16 logit-gradients are all zero "

@@ -24,7 +24,8 @@ namespace {
 constexpr int kStages = 6;
 constexpr int kBytesA = kBK * 128 * 2;          // 16 KB: 64 v x 128 k (this CTA's hidden units)
 constexpr int kBytesB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's 128 of the item's 256 cells x 64 v
-constexpr int kNumThreads = 192;
+constexpr int kEpiSets = 2;                       // epilogue warp sets; set e handles lattice tile e of the item
+constexpr int kNumThreads = 64 + 128 * kEpiSets;
 constexpr int kTmemCols = 512;
 
 struct SmemLayout {
@@ -61,7 +62,7 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     tma_prefetch_desc(&tmG);
     tma_prefetch_desc(&tmWmn);
     for (int s = 0; s < kStages; ++s) { mbar_init(full + 8 * s, 2); mbar_init(empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + 8 * s, 1); mbar_init(tmem_empty + 8 * s, 8 * kEpiSets); }
     mbar_fence_init();
   }
   if (warp == 1) { tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols); tmem_relinquish_pair(); }
@@ -119,6 +120,7 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
    }
   } else {
     const int lane_grp = warp & 3;
+    const int eset = (warp - 2) >> 2;
     const int krow = lane_grp * 32 + lane;      // hidden unit within the block = TMEM lane
     const float inv_s = __ldg(p.gscale + 1);
     uint32_t ic = 0;
@@ -131,7 +133,7 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       mbar_wait(tmem_full + 8 * acc, accph);
       tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      for (int half = eset; half < 2; half += kEpiSets) {
         const int slot = p.tile_begin + cb * 2 + half;
         if (slot >= tile_end) break;            // uniform
         const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, __ldg(p.tile_list + slot));
