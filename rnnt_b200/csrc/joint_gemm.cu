@@ -140,9 +140,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const uint32_t s = it % kStages, ph = (it / kStages) & 1;
             mbar_wait(empty + 8 * s, ph ^ 1);
             const uint32_t full_leader = mapa_shared(full + 8 * s, 0);
-            if (rank == 0) mbar_expect_tx(full + 8 * s, 2 * kStageBytes);   // both CTAs' boxes land on the leader's barrier
+            // (diagnostics: dbg bit 32 skips every other W load -- stale operands, used to measure what L2 traffic costs)
+            const bool skipw = (p.dbg & 32) && (it & 1);
+            if (rank == 0) mbar_expect_tx(full + 8 * s, 2 * kStageBytes - (skipw ? 2 * kBytesB : 0));   // both CTAs' boxes
             else mbar_arrive_cluster(full_leader);
-            tma_load_2d_pair(ring + s * kStageBytes, &tmW, full_leader, kc * kBK, pass * kBN + rank * (kBN / 2));
+            if (!skipw)
+              tma_load_2d_pair(ring + s * kStageBytes, &tmW, full_leader, kc * kBK, pass * kBN + rank * (kBN / 2));
             tma_load_2d_pair(ring + s * kStageBytes + kBytesB, &tmH, full_leader, kc * kBK, row0);
           }
         }
