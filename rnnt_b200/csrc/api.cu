@@ -231,7 +231,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
     a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles); a.tile_list = tile_list; a.n_active = n_active;
     { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
-    a.lp = nullptr; a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
+    a.lp = const_cast<float*>(lp); a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     a.h_out = h_src; a.h_map = h_map; a.g_ring = g_ring;
     rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, a, chunk_tiles, stream);
     if (rc) return rc;

@@ -54,6 +54,20 @@ struct SmemLayout {
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// v[idx] for a run-time idx in [0, 32) without local memory: a 5-level select tree (31 FSEL).
+__device__ __forceinline__ float pick32(const float (&v)[32], int idx) {
+  float a[16], b[8], c[4];
+  const bool s0 = idx & 1, s1 = idx & 2, s2 = idx & 4, s3 = idx & 8, s4 = idx & 16;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = s0 ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = s1 ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = s2 ? b[2 * i + 1] : b[2 * i];
+  const float d0 = s3 ? c[1] : c[0], d1 = s3 ? c[3] : c[2];
+  return s4 ? d1 : d0;
+}
+
 }  // namespace
 
 size_t joint_gemm_smem_bytes() { return SmemLayout::total + 1024; }
@@ -210,10 +224,19 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       float m = -INFINITY, ssum = 0.f, x_tgt = -INFINITY, x_blank = -INFINITY;
       // G state
       float gam = 0.f, eB = 0.f, eE = 0.f, lse2 = 1e30f, cbound = 0.f;
+      float g_blank = 0.f, g_tgt = 0.f;   // G: finished gradient values of the blank / label columns
       if (MODE == 1 && valid) {
         const float4 c4 = __ldg(p.coef + cell);
         gam = c4.x; eB = c4.y; eE = c4.z; lse2 = c4.w * kLog2e;
-        if (p.clamp > 0.f) cbound = p.clamp * fabsf(p.dcost ? __ldg(p.dcost + tc.b) : 1.f) * __ldg(p.gscale);
+        const float2 l = __ldg(reinterpret_cast<const float2*>(p.lp) + cell);   // log p(blank), log p(label)
+        g_blank = ex2_approx(l.x * kLog2e) * gam - eB;
+        g_tgt = ex2_approx(l.y * kLog2e) * gam - eE;
+        if (tgt == p.blank) g_tgt -= eB;     // (never the case for valid transcripts)
+        if (p.clamp > 0.f) {
+          cbound = p.clamp * fabsf(p.dcost ? __ldg(p.dcost + tc.b) : 1.f) * __ldg(p.gscale);
+          g_blank = fminf(fmaxf(g_blank, -cbound), cbound);
+          g_tgt = fminf(fmaxf(g_tgt, -cbound), cbound);
+        }
       }
       __half* g_row = nullptr;
       if (MODE == 1)
@@ -245,29 +268,15 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             const float m_new = fmaxf(m, cmax);
             float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              acc += ex2_approx(v[j] - m_new);
-              if (col0 + j == tgt) x_tgt = v[j];
-            }
+            for (int j = 0; j < 32; ++j) acc += ex2_approx(v[j] - m_new);
             ssum = ssum * ex2_approx(m - m_new) + acc;
             m = m_new;
-            if (p.blank >= col0 && p.blank < col0 + 32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j == p.blank) x_blank = v[j];
-            }
+            // label / blank logits: only the one chunk that holds the column pays for the selection
+            if (static_cast<unsigned>(tgt - col0) < 32u) x_tgt = pick32(v, tgt - col0);
+            if (static_cast<unsigned>(p.blank - col0) < 32u) x_blank = pick32(v, p.blank - col0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float g = ex2_approx(v[j] - lse2) * gam;
-              if (col0 + j == tgt) g -= eE;
-              v[j] = g;
-            }
-            if (p.blank >= col0 && p.blank < col0 + 32) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j == p.blank) v[j] -= eB;
-            }
+            for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j] - lse2) * gam;
             if (p.clamp > 0.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -cbound), cbound);
@@ -283,6 +292,10 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
               w.w = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
               dst[q] = w;
             }
+            // the two columns with one-hot terms are patched afterwards (same thread, program order): their softmax
+            // probabilities are exp(lp) from the forward, so no per-element comparison is needed in the loop above
+            if (static_cast<unsigned>(p.blank - col0) < 32u) g_row[p.blank] = __float2half_rn(g_blank);
+            if (static_cast<unsigned>(tgt - col0) < 32u) g_row[tgt] = __float2half_rn(g_tgt);
           }
         }
         tc_fence_before();

@@ -26,7 +26,7 @@ struct JointArgs {
   int tile_begin, tile_cap;   // process work-list slots [tile_begin, min(count, tile_begin + tile_cap))
   const int* tile_list;   // G: slot -> lattice tile (active tiles only); nullptr (F) = identity over all tiles
   const int* n_active;    // G: number of slots in tile_list
-  float* lp;              // F: (B,T,U1,2) log-probs (blank, label)
+  float* lp;              // F: output (B,T,U1,2) log-probs (blank, label); G: the same tensor, read-only
   float* lse;             // F: (B,T,U1) log-sum-exp of the logits (natural log)
   const float4* coef;     // G: (B,T,U1) (gamma*dc*S, eB*dc*S, eE*dc*S, lse)
   const float* dcost;     // G: (B) or nullptr (only used to scale the clamp bound)

@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-_DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(1 << 30)))
+_DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(3 << 30)))
 # Keep h = tanh(enc + pred) (fp16, 2*H bytes per lattice cell) from the forward for the backward (default), or
 # recompute it there (RNNT_B200_SAVE_HIDDEN=0: residuals shrink to 20 bytes per cell, the backward runs ~10 % slower).
 _SAVE_HIDDEN = os.environ.get("RNNT_B200_SAVE_HIDDEN", "1") != "0"
