@@ -214,13 +214,16 @@ def test_dense_loss_matches_torchaudio_and_golden(golden_dir):
         assert rel_err(lg.grad, l2.grad)[0] < 2e-4
 
 
-def test_lattice_kernel_vs_numpy_oracle():
+@pytest.mark.parametrize("shape", [(3, 23, 9), (3, 40, 33), (2, 37, 64), (3, 50, 101), (2, 30, 128), (2, 25, 150)])
+def test_lattice_kernel_vs_numpy_oracle(shape):
+    """Block sizes of 32 .. 160 threads (one thread per lattice column), ragged lengths incl. U_b = 0 and T_b = 1."""
     import rnnt_b200
     from oracle import rnnt_oracle as orc
     rng = np.random.default_rng(0)
-    B, T, U1 = 3, 23, 9
+    B, T, U1 = shape
     lp = np.log(rng.uniform(0.05, 0.9, size=(B, T, U1, 2))).astype(np.float32)
-    T_len = np.array([23, 11, 1], np.int32); U_len = np.array([8, 0, 5], np.int32)
+    T_len = np.array([T, max(1, T // 2), 1][:B], np.int32)
+    U_len = np.array([U1 - 1, 0, min(5, U1 - 1)][:B], np.int32)
     al, be, co = rnnt_b200.lattice(torch.from_numpy(lp).cuda(), torch.from_numpy(T_len).cuda(),
                                    torch.from_numpy(U_len).cuda())
     a_ref, b_ref, c_ref = orc.lattice(lp[..., 0].astype(np.float64), lp[..., 1].astype(np.float64), T_len, U_len)
@@ -229,6 +232,9 @@ def test_lattice_kernel_vs_numpy_oracle():
         sl = (b, slice(0, T_len[b]), slice(0, U_len[b] + 1))
         np.testing.assert_allclose(al.cpu().numpy()[sl], a_ref[sl], rtol=1e-5, atol=1e-4)
         np.testing.assert_allclose(be.cpu().numpy()[sl], b_ref[sl], rtol=1e-5, atol=1e-4)
+        # the two recursions agree on the total: -beta(0,0) == -(alpha(Tb-1,Ub) + lpB(Tb-1,Ub))
+        tail = al.cpu().numpy()[b, T_len[b] - 1, U_len[b]] + lp[b, T_len[b] - 1, U_len[b], 0]
+        assert abs(tail + co.cpu().numpy()[b]) < 1e-3 * max(1.0, abs(tail))
 
 
 def test_error_behaviour_mirrors_torchaudio():
