@@ -41,7 +41,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // (A suspend-time hint on try_wait was measured and rejected: wake-up latency rose so much that the forward kernel
-// went from 2.9 ms to 5.4 ms.)
+// went from 2.9 ms to 5.4 ms.  So were explicit .acquire.cluster / .release.cluster qualifiers on the barriers the
+// MMA issue loop touches: 1.6x slower; the default-scope forms below are what CUTLASS uses for CTA pairs, too.)
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -69,10 +70,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // pipeline hand-off slower -- the forward went from 2.9 ms to 5.8 ms -- so all lanes of a waiting warp poll.
 // A nanosleep back-off on the off-critical-path waits was neutral (3.27 vs 3.22 ms sustained) and was dropped.)
 
-// generic-proxy smem writes -> visible to the async proxy (TMA store / tcgen05.mma operand reads)
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -88,22 +85,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap,
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(tmap)),
-               "r"(smem_src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_all() {
-  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result_addr, uint32_t ncols) {
@@ -171,31 +152,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
-               "r"(bytes)
-               : "memory");
-}
-// wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > (1u << 24)) {
-      printf("rnnt_b200: cluster mbarrier timeout block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
 }
 // TMA load whose completion is signalled on an mbarrier of either CTA of the pair (`bar_cluster_addr`)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0,
@@ -286,26 +242,11 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-__device__ __forceinline__ float2 f16x2_to_f32(uint32_t packed) {
-  float lo, hi;
-  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
-      : "=f"(lo), "=f"(hi)
-      : "r"(packed));
-  return make_float2(lo, hi);
-}
-__device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
-__device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
-
 // tile -> utterance lookup: largest b with tile_off[b] <= tile (tile_off has B+1 entries)
 __device__ __forceinline__ int find_utt(const int* __restrict__ tile_off, int B, int tile) {
   int lo = 0, hi = B;  // invariant: tile_off[lo] <= tile < tile_off[hi]
