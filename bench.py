@@ -405,8 +405,10 @@ def run_gpu_arm(args):
         launches_dom = gemms[dom]["launches_per_step"]
         achieved = gemms[dom]["tflops"]
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
-        if os.path.exists(tpath):     # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+        import glob
+        tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+        tpath = tfiles[-1] if tfiles else ""
+        if tpath:     # DRAM bytes per launch of that kernel from the latest committed ncu --set full capture
             with open(tpath) as f:
                 traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
         roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
