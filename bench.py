@@ -435,8 +435,9 @@ def run_gpu_arm(args):
                                    "activation residual and the gradient ring through HBM",
                                 operands="fp16 x fp16 -> fp32 (TMEM), fp32 elsewhere",
                                 backward_tiles=dict(active=active_tiles, total=total_tiles, fraction=bwd_frac,
-                                                    note="lattice tiles whose fp16 logit-gradients are all zero "
-                                                         "(occupancy < 2^-25) are skipped; --all-tiles disables"),
+                                                    note="half-tiles (16 t x 4 u lattice blocks) whose fp16 logit-"
+                                                         "gradients are all zero (occupancy < 2^-25) are skipped; "
+                                                         "--all-tiles disables"),
                                 loss=loss_val),
                     clocks=clocks,
                     e2e=dict(value=cells_step / (e2e_ms * 1e-3 / args.steps), unit=UNIT,

@@ -36,7 +36,8 @@ const char* rnnt_b200_last_error(void);
 int64_t rnnt_b200_max_tiles(int B, int T, int U1);
 
 /* Size in bytes of the optional activation residual `hidden`: h = tanh(enc + pred) as fp16, one 128-row block per
- * lattice tile, rows padded to a multiple of 64 hidden units.  The reference's autograd saves the same tensor in fp32
+ * 16(t) x 8(u) lattice tile stored as two 16 x 4 half-tiles of 64 rows (row r of a half = cell (t0 + r/4,
+ * u0 + 4*half + r%4)), rows padded to a multiple of 64 hidden units.  The reference's autograd saves the same tensor in fp32
  * (rnnt/joint.py:37).  With it the backward does not recompute the tanh; without it (NULL) it does. */
 size_t rnnt_b200_hidden_bytes(int B, int T, int U1, int H);
 
@@ -64,8 +65,9 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
  * dcost (B) = d loss / d cost_b (1/B for reduction="mean"); clamp <= 0 disables gradient clamping.
  * hidden = the buffer the forward filled, or NULL to recompute the activations (memory-lean mode).
  * Outputs are overwritten: d_enc (B,T,H) contiguous, d_pred (B,U1,H), dW (V,H), dbias (V), all fp32.
- * Lattice tiles whose scaled logit-gradients are all below fp16 resolution (occupancy < 2^-25 of max|dcost|) are
- * exactly zero in the gradient ring and are skipped; flags bit 0 = 1 disables the skipping (every tile is processed). */
+ * Half-tiles (16 t x 4 u lattice blocks) whose scaled logit-gradients are all below fp16 resolution (occupancy < 2^-25
+ * of max|dcost|) are exactly zero in the gradient ring and are skipped; flags bit 0 = 1 disables the skipping (every
+ * half-tile that holds a valid cell is processed). */
 int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
                              const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
                              int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
@@ -122,12 +124,12 @@ int rnnt_b200_profile_begin(void);
 int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
 
 /* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
- *   offsets[0] tile table: B+1 int32 prefix sums of tiles per utterance, status, {S, 1/S} (fp32), n_active tiles
+ *   offsets[0] tile table: B+1 int32 prefix sums of tiles per utterance, status, {S, 1/S} (fp32), n_active half-tiles
  *   offsets[1] W as fp16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
  *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] fp16
  *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16 (-1 with have_hidden)
  *   offsets[6] bytes that satisfy both the forward and the backward call
- *   offsets[7] work list of active lattice tiles (int32).
+ *   offsets[7] work list of active half-tiles (int32 ids = 2 * tile + half); ring rows [64 i, 64 i + 64) = entry i.
  * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
 int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
                               int64_t* offsets /*[8]*/, int* Hp, int* Vp);

@@ -57,7 +57,8 @@ def lib() -> C.CDLL:
                     f"rnnt_b200: CUDA extension not built ({LIB_PATH} missing) and building it failed: {exc}. "
                     "Run `python -m rnnt_b200.build` (needs nvcc); there is no CPU or PyTorch fallback for this "
                     "path.") from exc
-        handle = C.CDLL(LIB_PATH)
+        # RNNT_B200_LIB: load another build of the same ABI (A/B timing of kernel variants); the default is the in-tree one
+        handle = C.CDLL(os.environ.get("RNNT_B200_LIB") or LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(handle, name)   # AttributeError if the symbol is not exported
             fn.restype = res

@@ -38,8 +38,8 @@ WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, bool 
   off = common;      // the backward re-uses the region after the converted weights
   w.coef = off;     off = align_up(off + static_cast<size_t>(B) * T * U1 * 16, 1024);
   const size_t max_tiles = static_cast<size_t>(B) * ((T + rb::kTileT - 1) / rb::kTileT) * ((U1 + rb::kTileU - 1) / rb::kTileU);
-  w.flags = off;    off = align_up(off + max_tiles, 1024);
-  w.tile_list = off; off = align_up(off + max_tiles * sizeof(int), 1024);
+  w.flags = off;    off = align_up(off + 2 * max_tiles, 1024);                     // one per half-tile
+  w.tile_list = off; off = align_up(off + 2 * max_tiles * sizeof(int), 1024);     // work list of half-tile ids
   const size_t ring_rows = static_cast<size_t>(ring_tiles) * kTileM;
   w.g_ring = off;   off = align_up(off + ring_rows * w.Vp * 2, 1024);
   w.h_ring = off;   off = align_up(off + (have_hidden ? 0 : ring_rows * w.Hp * 2), 1024);
@@ -133,10 +133,12 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   // small per-CTA scratch when no backward will follow
   __half* hbuf = hidden ? static_cast<__half*>(hidden) : reinterpret_cast<__half*>(ws + w.h_scratch);
   const uint64_t hrows = static_cast<uint64_t>(hidden ? max_tiles : w.scratch_tiles) * kTileM;
-  CUtensorMap tmW, tmH;
+  CUtensorMap tmW, tmH, tmH2;
   rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
-  rc = rb::make_tmap_2d(&tmH, hbuf, 2, w.Hp, hrows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
+  rc = rb::make_tmap_2d(&tmH, hbuf, 2, w.Hp, hrows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmH2, hbuf, 2, w.Hp, hrows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
 
   rb::JointArgs a{};
@@ -145,11 +147,11 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
   a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
   a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
-  a.tile_begin = 0; a.tile_cap = 0x3fffffff; a.tile_list = nullptr; a.n_active = nullptr;
+  a.slot_begin = 0; a.slot_cap = 0x3fffffff; a.sub_list = nullptr; a.n_active = nullptr;
   { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
   a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
   a.h_out = hbuf; a.h_map = hidden ? 0 : 2; a.g_ring = nullptr;
-  rc = rb::launch_joint_gemm(0, true, tmW, tmH, a, max_tiles, stream);
+  rc = rb::launch_joint_gemm(0, true, tmW, tmH, tmH2, a, 2 * max_tiles, stream);
   if (rc) return rc;
   return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
 }
@@ -196,21 +198,23 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   rc = rb::launch_coef(lp, lse, alpha, beta, dcost, gscale, T_len, U_len, B, T, U1, coef, stream);
   if (rc) return rc;
   int* n_active = tile_off + B + 4;
-  int* tile_list = reinterpret_cast<int*>(ws + w.tile_list);
+  int* sub_list = reinterpret_cast<int*>(ws + w.tile_list);    // active half-tiles, order preserved
   rc = rb::launch_tile_activity(coef, T_len, U_len, tile_off, B, T, U1, max_tiles, (flags & 1) ? 1 : 0,
-                                reinterpret_cast<unsigned char*>(ws + w.flags), tile_list, n_active, stream);
+                                reinterpret_cast<unsigned char*>(ws + w.flags), sub_list, n_active, stream);
   if (rc) return rc;
 
   const uint64_t h_rows = hidden ? static_cast<uint64_t>(max_tiles) * kTileM : ring_rows;
-  CUtensorMap tmW, tmWmn, tmG128, tmHk, tmGmn, tmHmn;
+  CUtensorMap tmW, tmWmn, tmG128, tmHk, tmHk2, tmGmn, tmHmn;
   // W [Vp, Hp]: K-major boxes (64 k x 128 v) for the recompute, MN-major boxes (64 k_h x 64 v) for dh
   rc = rb::make_tmap_2d(&tmW, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmWmn, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
-  // activations: 64 x 128 K-major boxes for the logit recompute, 64 x 64 boxes for the MN-major dW operand;
+  // activations: 64 x 64 boxes (one half-tile), K-major for the logit recompute and MN-major for the dW operand;
   // gradient ring: 64 x 128 K-major boxes for dh (one lattice tile per CTA of a pair), 64 x 64 boxes for the MN-major dW operand
-  rc = rb::make_tmap_2d(&tmHk, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
+  rc = rb::make_tmap_2d(&tmHk, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
+  if (rc) return rc;
+  rc = rb::make_tmap_2d(&tmHk2, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmG128, g_ring, 2, w.Vp, ring_rows, static_cast<uint64_t>(w.Vp) * 2, 64, 128);
   if (rc) return rc;
@@ -219,37 +223,39 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   rc = rb::make_tmap_2d(&tmHmn, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
 
-  const int64_t nchunks = (max_tiles + ring_tiles - 1) / ring_tiles;
+  // the work list is walked in chunks of as many slots (half-tiles of 64 rows) as the ring holds
+  const int64_t max_slots = 2 * max_tiles, ring_slots = 2 * ring_tiles;
+  const int64_t nchunks = (max_slots + ring_slots - 1) / ring_slots;
   for (int64_t c = 0; c < nchunks; ++c) {
-    const int tile_begin = static_cast<int>(c * ring_tiles);
-    const int64_t chunk_tiles = std::min<int64_t>(ring_tiles, max_tiles - c * ring_tiles);
+    const int slot_begin = static_cast<int>(c * ring_slots);
+    const int64_t chunk_slots = std::min<int64_t>(ring_slots, max_slots - c * ring_slots);
     rb::JointArgs a{};
     a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st;
     a.pred = pred; a.pred_sb = static_cast<long long>(U1) * H; a.pred_su = H;
     a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
     a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
     a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
-    a.tile_begin = tile_begin; a.tile_cap = static_cast<int>(ring_tiles); a.tile_list = tile_list; a.n_active = n_active;
+    a.slot_begin = slot_begin; a.slot_cap = static_cast<int>(ring_slots); a.sub_list = sub_list; a.n_active = n_active;
     { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
     a.lp = const_cast<float*>(lp); a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     a.h_out = h_src; a.h_map = h_map; a.g_ring = g_ring;
-    rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, a, chunk_tiles, stream);
+    rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, tmHk2, a, chunk_slots, stream);
     if (rc) return rc;
 
     rb::DhArgs d{};
     d.enc = enc; d.enc_sb = enc_sb; d.enc_st = enc_st;
-    d.pred = pred; d.pred_sb = static_cast<long long>(U1) * H; d.pred_su = H; d.gscale = gscale; d.tile_list = tile_list; d.n_active = n_active;
+    d.pred = pred; d.pred_sb = static_cast<long long>(U1) * H; d.pred_su = H; d.gscale = gscale; d.sub_list = sub_list; d.n_active = n_active;
     d.T_len = T_len; d.U_len = U_len; d.tile_off = tile_off;
     d.B = B; d.T = T; d.U1 = U1; d.H = H; d.Hp = w.Hp; d.Vp = w.Vp;
-    d.tile_begin = tile_begin; d.tile_cap = static_cast<int>(ring_tiles);
+    d.slot_begin = slot_begin; d.slot_cap = static_cast<int>(ring_slots);
     d.d_enc = d_enc; d.d_pred = d_pred;
-    rc = rb::launch_dh_gemm(tmG128, tmWmn, d, chunk_tiles, stream);
+    rc = rb::launch_dh_gemm(tmG128, tmWmn, d, chunk_slots, stream);
     if (rc) return rc;
 
     rb::DwArgs g{};
-    g.n_active = n_active; g.tile_list = tile_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
-    g.tile_begin = tile_begin; g.tile_cap = static_cast<int>(ring_tiles); g.dW = dW; g.db = dbias; g.gscale = gscale;
-    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_tiles, stream);
+    g.n_active = n_active; g.sub_list = sub_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
+    g.slot_begin = slot_begin; g.slot_cap = static_cast<int>(ring_slots); g.dW = dW; g.db = dbias; g.gscale = gscale;
+    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_slots, stream);
     if (rc) return rc;
   }
   return 0;

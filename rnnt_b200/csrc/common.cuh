@@ -14,10 +14,14 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 // ---------------------------------------------------------------------------------------------
 // Tile geometry shared by every kernel of the path (see DESIGN.md "Tile map").
-// A tile is a 16(t) x 8(u) block of one utterance's lattice = 128 GEMM rows; row r <-> (r>>3, r&7).
+// A tile is a 16(t) x 8(u) block of one utterance's lattice = 128 GEMM rows, stored as two HALF-TILES of 16(t) x 4(u)
+// = 64 rows each (row r of a half <-> (t0 + (r>>2), u0 + 4*half + (r&3))).  Half-tile id = 2 * tile + half.  The
+// backward's work list, the gradient ring and the activation buffer are all organised in half-tiles.
 constexpr int kTileT = 16;
 constexpr int kTileU = 8;
 constexpr int kTileM = 128;
+constexpr int kHalfU = 4;
+constexpr int kHalfRows = 64;
 constexpr int kBK = 64;     // K chunk: 64 bf16 = one 128-byte swizzle row
 constexpr int kBN = 256;    // N per MMA instruction / accumulator / B stage
 
@@ -270,6 +274,14 @@ __device__ __forceinline__ TileCoord decode_tile(const int* __restrict__ tile_of
   int local = tile - __ldg(tile_off + c.b);
   c.t0 = (local / nu) * kTileT;
   c.u0 = (local % nu) * kTileU;
+  return c;
+}
+
+// half-tile id -> coordinates; u0 is the first column of the HALF (tile u0 + 4 * half)
+__device__ __forceinline__ TileCoord decode_half(const int* __restrict__ tile_off, const int* __restrict__ T_len,
+                                                 const int* __restrict__ U_len, int B, int half_id) {
+  TileCoord c = decode_tile(tile_off, T_len, U_len, B, half_id >> 1);
+  c.u0 += (half_id & 1) * kHalfU;
   return c;
 }
 

@@ -4,13 +4,13 @@
 // Replaces autograd through rnnt/joint.py:32-39 for the activations:
 //   dz[c,k]       = dh[c,k] * (1 - tanh(enc[b,t,k] + pred[b,u,k])^2)
 //   d_enc[b,t,k]  = sum_u dz[b,t,u,k]      d_pred[b,u,k] = sum_t dz[b,t,u,k]
-// Putting the hidden unit on the TMEM lane makes a thread own ONE k and 32 consecutive cells (= 4 t x 8 u of a
-// lattice tile) per tcgen05.ld: both reductions are plain register sums, tanh' is recomputed from 4 enc + 8 pred
+// Putting the hidden unit on the TMEM lane makes a thread own ONE k and 32 consecutive cells (= 8 t x 4 u of a
+// half-tile) per tcgen05.ld: both reductions are plain register sums, tanh' is recomputed from 8 enc + 4 pred
 // values per thread (MUFU is otherwise idle here), and the fp32 atomics are coalesced over k.
 //   A operand: W^T block (128 k x 64 v) = MN-major view of the fp16 W[Vp,Hp] buffer (TMA, two 64x64 boxes)
 //   B operand: gradient ring g [ring_rows, Vp] fp16, K-major (TMA, one 64 x 256 box = two lattice tiles)
-// Work item of a CTA PAIR = (two lattice tiles = 256 cells, block of 256 hidden units): one tcgen05.mma.cta_group::2
-// with M = 256; each CTA stages its own 128 hidden units of W^T and HALF of the gradient box (one lattice tile), so
+// Work item of a CTA PAIR = (four half-tiles of the work list = 256 cells, block of 256 hidden units): one tcgen05.mma.cta_group::2
+// with M = 256; each CTA stages its own 128 hidden units of W^T and HALF of the gradient box (two half-tiles), so
 // the L2 -> shared-memory traffic is 64 instead of 96 bytes per SM and clock.  Accumulators ping-pong between the two
 // halves of TMEM so the epilogue of item i overlaps the MMAs of item i+1.
 #include <algorithm>
@@ -50,10 +50,10 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-  const int total_tiles = __ldg(p.n_active);
-  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots
-  const int ntiles = max(0, tile_end - p.tile_begin);
-  const int ncb = (ntiles + 1) / 2;                 // cell blocks of 2 lattice tiles (256 ring rows)
+  const int total_slots = __ldg(p.n_active);
+  const int slot_end = min(total_slots, p.slot_begin + p.slot_cap);   // work-list slots (half-tiles)
+  const int nslots = max(0, slot_end - p.slot_begin);
+  const int ncb = (nslots + 3) / 4;                 // cell blocks of 4 half-tiles (256 ring rows)
   const int nhb = (p.Hp + 255) / 256;               // hidden blocks of 256 (128 per CTA of the pair)
   const int nitems = ncb * nhb;
   const int nk = p.Vp / kBK;
@@ -133,43 +133,43 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       mbar_wait(tmem_full + 8 * acc, accph);
       tc_fence_after();
 #pragma unroll 1
-      for (int half = eset; half < 2; half += kEpiSets) {
-        const int slot = p.tile_begin + cb * 2 + half;
-        if (slot >= tile_end) break;            // uniform
-        const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, __ldg(p.tile_list + slot));
-        float pv[8], su[8];
+      for (int hs = eset * (4 / kEpiSets); hs < (eset + 1) * (4 / kEpiSets); ++hs) {   // this set's half-tiles of the item
+        const int slot = p.slot_begin + cb * 4 + hs;
+        if (slot >= slot_end) break;            // uniform
+        const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, __ldg(p.sub_list + slot));
+        float pv[4], su[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           pv[j] = __ldg(p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + j, p.U1 - 1)) * p.pred_su + kk);
           su[j] = 0.f;
         }
         const float* e_base = p.enc + tc.b * p.enc_sb + kk;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {           // 32 columns = t-rows 8q .. 8q+7 x 4 u
           float v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * kBN + half * 128 + q * 32, v);
-          float ev[4];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * kBN + hs * 64 + q * 32, v);
+          float ev[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            ev[i] = __ldg(e_base + static_cast<long long>(min(tc.t0 + q * 4 + i, p.T - 1)) * p.enc_st);
+          for (int i = 0; i < 8; ++i)
+            ev[i] = __ldg(e_base + static_cast<long long>(min(tc.t0 + q * 8 + i, p.T - 1)) * p.enc_st);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 8; ++i) {
             float st = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               const float h = tanh_approx(ev[i] + pv[j]);
-              const float dz = v[i * 8 + j] * fmaf(-h, h, 1.f);
+              const float dz = v[i * 4 + j] * fmaf(-h, h, 1.f);
               st += dz;
               su[j] += dz;
             }
-            const int t = tc.t0 + q * 4 + i;
+            const int t = tc.t0 + q * 8 + i;
             if (k_ok && t < tc.Tb)
               atomicAdd(p.d_enc + (static_cast<long long>(tc.b) * p.T + t) * p.H + k, st * inv_s);
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           const int u = tc.u0 + j;
           if (k_ok && u <= tc.Ub)
             atomicAdd(p.d_pred + (static_cast<long long>(tc.b) * p.U1 + u) * p.H + k, su[j] * inv_s);
@@ -189,12 +189,12 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
 
 }  // namespace
 
-int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, long long chunk_tiles,
+int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, long long chunk_slots,
                    cudaStream_t stream) {
   ProfScope prof_(kProfDh, stream);
   const size_t smem = SmemLayout::total + 1024;
   RB_CUDA_CHECK(cudaFuncSetAttribute(dh_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long items = ((chunk_tiles + 1) / 2) * ((args.Hp + 255) / 256);
+  const long long items = ((chunk_slots + 3) / 4) * ((args.Hp + 255) / 256);
   const int pairs = max_cta_pairs(reinterpret_cast<const void*>(dh_gemm_kernel), kNumThreads, smem);
   const int grid = 2 * static_cast<int>(std::max<long long>(1, std::min<long long>(pairs, items)));
   dh_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmG, tmWmn, args);

@@ -46,9 +46,9 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int total_tiles = __ldg(p.n_active);
-  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);
-  const int nkc = max(0, tile_end - p.tile_begin) * (kTileM / kBK);   // 64-row K chunks in this ring chunk
+  const int total_slots = __ldg(p.n_active);
+  const int slot_end = min(total_slots, p.slot_begin + p.slot_cap);
+  const int nkc = max(0, slot_end - p.slot_begin);   // K chunks of 64 cells = work-list slots (half-tiles) of this ring chunk
 
   const int nblk_total = (p.Hp + kBN - 1) / kBN;
   const int nht = (nblk_total + 1) / 2;
@@ -95,10 +95,8 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
         for (int j = 0; j < 2; ++j)
           tma_load_2d(a_ring + sa * kBytesA + j * 8192, &tmGmn, a_full + 8 * sa,
                       (vt * 2 + rank) * kTileM + j * 64, kc * kBK);
-        // activation rows of this 64-cell chunk: ring rows, or the forward's residual buffer (tile-indexed)
-        const int hrow = (p.h_map == 0)
-                             ? __ldg(p.tile_list + p.tile_begin + (kc >> 1)) * kTileM + (kc & 1) * kBK
-                             : kc * kBK;
+        // activation rows of this 64-cell chunk: ring rows, or the forward's residual buffer (indexed by half-tile)
+        const int hrow = (p.h_map == 0) ? __ldg(p.sub_list + p.slot_begin + kc) * kHalfRows : kc * kBK;
         for (int blk = 0; blk < nblk; ++blk, ++itb) {
           const uint32_t sb = itb % kStagesB, phb = (itb / kStagesB) & 1;
           mbar_wait(b_empty + 8 * sb, phb ^ 1);
@@ -213,7 +211,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
 
 }  // namespace
 
-int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args_in, long long chunk_tiles,
+int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args_in, long long chunk_slots,
                    cudaStream_t stream) {
   ProfScope prof_(kProfDw, stream);
   const size_t smem = SmemLayout::total + 1024;
@@ -222,7 +220,7 @@ int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwA
   const int nblk_total = (args.Hp + kBN - 1) / kBN;
   const int out_blocks = (args.Vp / (2 * kTileM)) * ((nblk_total + 1) / 2);   // 256 x 512 blocks of dW, one pair each
   const int pairs = max_cta_pairs(reinterpret_cast<const void*>(dw_gemm_kernel), kNumThreads, smem);
-  const long long kchunks = chunk_tiles * (kTileM / kBK);
+  const long long kchunks = chunk_slots;
   args.ksplit = static_cast<int>(std::max<long long>(1, std::min<long long>(pairs / std::max(1, out_blocks), kchunks)));
   const int grid = 2 * out_blocks * args.ksplit;
   dw_gemm_kernel<<<grid, kNumThreads, smem, stream>>>(tmGmn, tmHmn, args);

@@ -9,8 +9,10 @@
 // (fp16 operands: tanh output lies in [-1,1] and joint weights are O(1), so fp16's 11-bit mantissa gives 8x
 // finer rounding than bf16 at the same tensor-core rate; accumulation is fp32 in TMEM.)
 //
-// Structure (persistent CTA PAIRS, one CTA per SM; work unit per CTA = 16(t) x 8(u) lattice tile = 128 GEMM rows, the
-// two tiles of a pair form one M=256 tcgen05.mma.cta_group::2 issued by the pair's leader):
+// Structure (persistent CTA PAIRS, one CTA per SM; work unit per CTA = 128 GEMM rows = TWO half-tiles of 16(t) x 4(u)
+// lattice cells -- in the forward the two halves of one 16 x 8 tile, in the backward any two entries of the list of
+// half-tiles that carry non-zero gradients; the two 128-row units of a pair form one M=256 tcgen05.mma.cta_group::2
+// issued by the pair's leader):
 //   * The hidden activations h = tanh(enc+pred) of a tile are produced ONCE, as fp16 rows of a global buffer
 //     (the residual the backward re-uses, or a small per-CTA scratch), by 8 producer warps that run one to two
 //     tiles AHEAD of the tensor pipe.  They are decoupled from the MMA pipeline: no shared-memory staging, no
@@ -75,7 +77,8 @@ int joint_gemm_scratch_tiles(int grid) { return grid * kScratchSlots; }
 
 template <int MODE, bool PRODUCE>  // MODE 0 = forward (lse + gather), 1 = backward (gradient ring)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PRODUCE ? kThreadsProd : kThreadsNoProd, 1)
-joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH, JointArgs p) {
+joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
+                  const __grid_constant__ CUtensorMap tmH2, JointArgs p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -94,21 +97,30 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair (issues the MMAs)
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
-  const int total_tiles = p.n_active ? __ldg(p.n_active) : __ldg(p.tile_off + p.B);
-  const int tile_end = min(total_tiles, p.tile_begin + p.tile_cap);   // work-list slots [tile_begin, tile_end)
+  // work list: slots of 64 rows (half-tiles); identity over all half-tiles in the forward
+  const int total_slots = p.n_active ? __ldg(p.n_active) : 2 * __ldg(p.tile_off + p.B);
+  const int slot_end = min(total_slots, p.slot_begin + p.slot_cap);   // this launch: slots [slot_begin, slot_end)
+  const int nunits = (max(0, slot_end - p.slot_begin) + 1) >> 1;      // 128-row units = pairs of consecutive slots
   const int nk = p.Hp / kBK;
   const int npass = p.Vp / kBN;
 
-  // row block of the activation buffer that holds the tile of work-list slot `slot` (the cnt-th tile of this CTA)
-  auto h_row0 = [&](int slot, int tile, uint32_t cnt) -> int {
-    if (p.h_map == 0) return tile * kTileM;                       // full buffer, indexed by lattice tile
-    if (p.h_map == 1) return (slot - p.tile_begin) * kTileM;      // backward ring, indexed by slot of this chunk
-    return (static_cast<int>(blockIdx.x) * kScratchSlots + static_cast<int>(cnt % kScratchSlots)) * kTileM;
+  // half-tile id (2 * lattice tile + half) of sub-slot s of unit q, or -1 past the end of the list
+  auto half_id = [&](int q, int s) -> int {
+    const int slot = p.slot_begin + 2 * q + s;
+    if (q >= nunits || slot >= slot_end) return -1;
+    return p.sub_list ? __ldg(p.sub_list + slot) : slot;
+  };
+  // first row of the activation buffer that holds sub-slot s of unit q (the cnt-th unit of this CTA)
+  auto h_row0 = [&](int q, int s, int hid, uint32_t cnt) -> int {
+    if (p.h_map == 0) return hid * kHalfRows;                     // full buffer, indexed by half-tile
+    if (p.h_map == 1) return (2 * q + s) * kHalfRows;             // backward ring, indexed by slot of this chunk
+    return (static_cast<int>(blockIdx.x) * kScratchSlots + static_cast<int>(cnt % kScratchSlots)) * kTileM + s * kHalfRows;
   };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmH2);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full + 8 * s, 2);        // leader's copy: one expect_tx arrival per CTA of the pair
       mbar_init(empty + 8 * s, 1);
@@ -131,20 +143,22 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-// this CTA's tiles: slot = base + rank for base = tile_begin + 2 * (pair + i * npairs); a pair whose second slot is past
-// the end still runs (the leader's MMA spans both CTAs) with that CTA's outputs suppressed
-#define RB_TILE_LOOP(cntvar)                                                                                    \
-  for (int base_ = p.tile_begin + 2 * pair; base_ < tile_end; base_ += 2 * npairs, ++cntvar)
+// this CTA's units: q = base + rank for base = 2 * (pair + i * npairs); a pair whose second unit is past the end still
+// runs (the leader's MMA spans both CTAs) with that CTA's outputs suppressed
+#define RB_TILE_LOOP(cntvar) for (int base_ = 2 * pair; base_ < nunits; base_ += 2 * npairs, ++cntvar)
 
   if (warp == 0) {
     // ===================================================================== TMA loader (W boxes + activation boxes)
     if (lane == 0) {
       uint32_t it = 0, cnt = 0;
       RB_TILE_LOOP(cnt) {
-        const int slot = base_ + rank;
-        const bool mine = slot < tile_end;
-        const int tile = !mine ? 0 : (p.tile_list ? __ldg(p.tile_list + slot) : slot);
-        const int row0 = mine ? h_row0(slot, tile, cnt) : 0;   // no tile: any resident row block (results unused)
+        const int q = base_ + rank;
+        int hrow[2];
+#pragma unroll
+        for (int sh = 0; sh < 2; ++sh) {
+          const int hid = half_id(q, sh);
+          hrow[sh] = hid >= 0 ? h_row0(q, sh, hid, cnt) : 0;     // nothing there: any resident rows (results unused)
+        }
         if (PRODUCE) {
           mbar_wait(h_ready + 8 * (cnt & 1), (cnt >> 1) & 1);
           fence_proxy_async_all();   // the producers' generic-proxy global stores -> TMA (async proxy) reads
@@ -160,7 +174,12 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             else mbar_arrive_cluster(full_leader);
             if (!skipw)
               tma_load_2d_pair(ring + s * kStageBytes, &tmW, full_leader, kc * kBK, pass * kBN + rank * (kBN / 2));
-            tma_load_2d_pair(ring + s * kStageBytes + kBytesB, &tmH, full_leader, kc * kBK, row0);
+            if (hrow[1] == hrow[0] + kHalfRows) {     // both halves of one tile / adjacent ring slots: one 128-row box
+              tma_load_2d_pair(ring + s * kStageBytes + kBytesB, &tmH2, full_leader, kc * kBK, hrow[0]);
+            } else {
+              tma_load_2d_pair(ring + s * kStageBytes + kBytesB, &tmH, full_leader, kc * kBK, hrow[0]);
+              tma_load_2d_pair(ring + s * kStageBytes + kBytesB + kBytesA / 2, &tmH, full_leader, kc * kBK, hrow[1]);
+            }
           }
         }
       }
@@ -206,17 +225,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int lane_grp = warp & 3;  // TMEM lane quarter this warp may access
     const int eset = (warp - kFirstEpiWarp) >> 2;
     const int row = lane_grp * 32 + lane;
-    const int ti = row >> 3, ui = row & 7;
+    const int sub = row >> 6;                     // which of the unit's two half-tiles this row belongs to
+    const int ti = (row & 63) >> 2, ui = row & 3;
     float4* xchg = reinterpret_cast<float4*>(smem_gen + SL::xchg);
     const uint32_t tmem_empty_leader = mapa_shared(tmem_empty + 8 * eset, 0);
     uint32_t pc = 0, tcount = 0;
     RB_TILE_LOOP(tcount) {
-      const int slot = base_ + rank;
-      const bool mine = slot < tile_end;
-      const int tile = !mine ? 0 : (p.tile_list ? __ldg(p.tile_list + slot) : slot);
-      const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
+      const int q = base_ + rank;
+      const bool mine = q < nunits;
+      const int hid = half_id(q, sub);
+      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, max(hid, 0));
       const int t = tc.t0 + ti, u = tc.u0 + ui;
-      const bool valid = mine && (t < tc.Tb) && (u <= tc.Ub);
+      const bool valid = hid >= 0 && (t < tc.Tb) && (u <= tc.Ub);
       const long long cell = (static_cast<long long>(tc.b) * p.T + min(t, p.T - 1)) * p.U1 + min(u, p.U1 - 1);
       int tgt = -1;
       if (valid && u < tc.Ub) tgt = __ldg(p.targets + static_cast<long long>(tc.b) * p.tgt_ld + u);
@@ -240,7 +260,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       }
       __half* g_row = nullptr;
       if (MODE == 1)
-        g_row = p.g_ring + (static_cast<long long>(slot - p.tile_begin) * kTileM + row) * p.Vp;
+        g_row = p.g_ring + (static_cast<long long>(q) * kTileM + row) * p.Vp;
 
       for (int pass = 0; pass < npass; ++pass, ++pc) {
         if (static_cast<int>(pc & 1) != eset) continue;
@@ -322,60 +342,61 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   } else if (PRODUCE && warp >= kFirstProdWarp) {
     // ===================================================================== activation producers
-    // Warp rg produces rows rg*16 .. rg*16+15 of the tile (t-rows 2rg, 2rg+1; all 8 u).  Lane l owns the 16-byte
-    // column chunk c = l & 7 (8 hidden units) of the four rows (t-row 0|1) x (u = rs | rs+4), rs = l >> 3:
-    // 4 x 8 inputs -> 32 tanh -> four 16-byte global stores; the 8 lanes of one row write 128 contiguous bytes.
+    // Warp rg produces rows rg*16 .. rg*16+15 of the unit = t-rows 4(rg&3) .. +3 x 4 u of half-tile rg>>2.  Lane l owns
+    // the 16-byte column chunk c = l & 7 (8 hidden units) of the four rows (t-row 2(rs>>1) + i) x (u = 2(rs&1) + j),
+    // rs = l >> 3: (2 + 2) x 8 inputs -> 32 tanh -> four 16-byte global stores; the 8 lanes of one row write 128
+    // contiguous bytes.
     const int rg = warp - kFirstProdWarp;
     const int c = lane & 7, rs = lane >> 3;
+    const int sub = rg >> 2, tq = (rg & 3) * 4 + (rs >> 1) * 2, uq = (rs & 1) * 2;
     uint32_t cnt = 0;
     RB_TILE_LOOP(cnt) {
-      const int slot = base_ + rank;
-      if (slot >= tile_end) {            // the pair's odd tile out: nothing to produce, keep the barrier protocol
+      const int q = base_ + rank;
+      const int hid = half_id(q, sub);
+      if (hid < 0) {            // nothing to produce for this half: keep the barrier protocol
         if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(h_ready + 8 * (cnt & 1));
         continue;
       }
-      const int tile = p.tile_list ? __ldg(p.tile_list + slot) : slot;
-      const TileCoord tc = decode_tile(p.tile_off, p.T_len, p.U_len, p.B, tile);
-      const int row0 = h_row0(slot, tile, cnt);
+      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, hid);
+      const int row0 = h_row0(q, sub, hid, cnt);
       const float* e_ptr[2];
       const float* p_ptr[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + 2 * rg + i, p.T - 1)) * p.enc_st + 8 * c;
-        p_ptr[i] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + rs + 4 * i, p.U1 - 1)) * p.pred_su + 8 * c;
+        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + tq + i, p.T - 1)) * p.enc_st + 8 * c;
+        p_ptr[i] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + uq + i, p.U1 - 1)) * p.pred_su + 8 * c;
       }
       float4 e_cur[2][2], p_cur[2][2];
-      auto load_chunk = [&](int kc, float4 (&e)[2][2], float4 (&q)[2][2]) {
+      auto load_chunk = [&](int kc, float4 (&e)[2][2], float4 (&pp)[2][2]) {
         const int col = kc * kBK + 8 * c;
         if (col < p.H) {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             e[i][0] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK));
             e[i][1] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK) + 1);
-            q[i][0] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK));
-            q[i][1] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK) + 1);
+            pp[i][0] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK));
+            pp[i][1] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK) + 1);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            e[i][0] = e[i][1] = q[i][0] = q[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int i = 0; i < 2; ++i) e[i][0] = e[i][1] = pp[i][0] = pp[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
       load_chunk(0, e_cur, p_cur);
-      // stay at most two tiles ahead of the tensor pipe: tile cnt-2 must be fully consumed (also keeps the
+      // stay at most two units ahead of the tensor pipe: unit cnt-2 must be fully consumed (also keeps the
       // two-phase h_ready / tile_done barriers and the 4-slot scratch unambiguous)
       if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
-      __half* out_base = p.h_out + static_cast<long long>(row0 + rg * 16) * p.Hp + 8 * c;
+      // row of (t-row tq + i, u = uq + j) inside the half-tile: (tq + i) * 4 + uq + j
+      __half* out_base = p.h_out + static_cast<long long>(row0 + tq * 4 + uq) * p.Hp + 8 * c;
       for (int kc = 0; kc < nk; ++kc) {
         if (p.dbg & 2) break;   // diagnostics: leave the buffer's previous contents (valid data from an earlier call)
         uint4 w[2][2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {        // t-row
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {      // u = rs + 4j
+          for (int j = 0; j < 2; ++j) {      // u
             const float4 a0 = e_cur[i][0], a1 = e_cur[i][1], b0 = p_cur[j][0], b1 = p_cur[j][1];
             w[i][j].x = pack_f16x2(tanh_approx(a0.x + b0.x), tanh_approx(a0.y + b0.y));
             w[i][j].y = pack_f16x2(tanh_approx(a0.z + b0.z), tanh_approx(a0.w + b0.w));
@@ -389,7 +410,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            *reinterpret_cast<uint4*>(out_base + static_cast<long long>(i * 8 + rs + 4 * j) * p.Hp + kc * kBK) = w[i][j];
+            *reinterpret_cast<uint4*>(out_base + static_cast<long long>(i * 4 + j) * p.Hp + kc * kBK) = w[i][j];
       }
       fence_proxy_async_all();   // generic-proxy global writes -> visible to the loader's TMA reads
       __syncwarp();
@@ -407,18 +428,18 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   }
 }
 
-int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
-                      long long max_tiles, cudaStream_t stream) {
+int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const CUtensorMap& tmH2,
+                      const JointArgs& args, long long max_slots, cudaStream_t stream) {
   ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
   const size_t smem = SmemLayout::total + 1024;
-  const long long want_pairs = std::max<long long>(1, (max_tiles + 1) / 2);
+  const long long want_pairs = std::max<long long>(1, (max_slots + 3) / 4);   // 2 slots per CTA, 2 CTAs per pair
 #define RB_LAUNCH_JG(M, P)                                                                                         \
   do {                                                                                                             \
     RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                        (int)smem));                                                                \
     const int grid = 2 * static_cast<int>(std::min<long long>(max_cta_pairs(reinterpret_cast<const void*>(joint_gemm_kernel<M, P>), P ? kThreadsProd : kThreadsNoProd, smem), want_pairs));                 \
     if (args.dbg & 8) fprintf(stderr, "rnnt_b200: joint gemm mode %d produce %d grid %d\n", M, (int)P, grid);       \
-    joint_gemm_kernel<M, P><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, args);            \
+    joint_gemm_kernel<M, P><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, tmH2, args);            \
   } while (0)
   if (mode == 0) {
     RB_REQUIRE(produce, -30, "forward joint kernel always produces the activations");

@@ -23,9 +23,9 @@ struct JointArgs {
   const int* U_len;
   const int* tile_off;    // [B+1] prefix sum of tiles per utterance; tile_off[B] = total
   int B, T, U1, H, Hp, V, Vp, blank;
-  int tile_begin, tile_cap;   // process work-list slots [tile_begin, min(count, tile_begin + tile_cap))
-  const int* tile_list;   // G: slot -> lattice tile (active tiles only); nullptr (F) = identity over all tiles
-  const int* n_active;    // G: number of slots in tile_list
+  int slot_begin, slot_cap;   // process work-list slots (half-tiles, 64 rows) [slot_begin, min(count, slot_begin + slot_cap))
+  const int* sub_list;    // G: slot -> half-tile id (active ones only); nullptr (F) = identity over all half-tiles
+  const int* n_active;    // G: number of slots in sub_list
   float* lp;              // F: output (B,T,U1,2) log-probs (blank, label); G: the same tensor, read-only
   float* lse;             // F: (B,T,U1) log-sum-exp of the logits (natural log)
   const float4* coef;     // G: (B,T,U1) (gamma*dc*S, eB*dc*S, eE*dc*S, lse)
@@ -33,8 +33,8 @@ struct JointArgs {
   const float* gscale;    // G: {S, 1/S} power-of-two gradient scale
   float clamp;            // G: <= 0 disables (torchaudio's clamp argument, rnnt/model.py:40 passes -1)
   __half* h_out;          // producers: activation rows h = tanh(enc+pred) as fp16 [rows, Hp] (same buffer tmH reads)
-  int h_map;              // row block of a tile in that buffer: 0 = tile*128 (saved residual), 1 = ring slot*128
-                          // (backward recompute), 2 = per-CTA scratch slot (forward without a residual buffer)
+  int h_map;              // rows of a half-tile in that buffer: 0 = half_id*64 (saved residual), 1 = ring slot*64
+                          // (backward recompute), 2 = per-CTA scratch (forward without a residual buffer)
   __half* g_ring;         // G: gradient ring [ring_tiles*128, Vp] fp16
   int dbg;                // diagnostics only (RNNT_B200_DBG): 1 = skip epilogue math, 2 = skip producer math
 };
@@ -45,24 +45,24 @@ struct DhArgs {
   const float* pred;      // (B,U1,H)
   long long pred_sb, pred_su;
   const float* gscale;    // {S, 1/S}
-  const int* tile_list;   // slot -> lattice tile; ring row block i holds tile_list[tile_begin + i]
+  const int* sub_list;    // slot -> half-tile id; ring rows [64 i, 64 i + 64) hold sub_list[slot_begin + i]
   const int* n_active;
   const int* T_len;
   const int* U_len;
   const int* tile_off;
   int B, T, U1, H, Hp, Vp;
-  int tile_begin, tile_cap;
+  int slot_begin, slot_cap;
   float* d_enc;          // (B,T,H) fp32, accumulated with atomics (caller zero-fills)
   float* d_pred;         // (B,U1,H)
 };
 
 struct DwArgs {
-  const int* n_active;   // number of work-list slots (ring rows of this chunk = slots in range * 128)
-  const int* tile_list;  // slot -> lattice tile (row block of the saved activations when h_map == 0)
-  int h_map;             // 0 = activations come from the forward's residual buffer (rows tile*128), 1 = from the ring
+  const int* n_active;   // number of work-list slots (ring rows of this chunk = slots in range * 64)
+  const int* sub_list;   // slot -> half-tile id (row block of the saved activations when h_map == 0)
+  int h_map;             // 0 = activations come from the forward's residual buffer (rows half_id*64), 1 = from the ring
   const int* tile_off;
   int B, H, Hp, V, Vp;
-  int tile_begin, tile_cap;
+  int slot_begin, slot_cap;
   float* dW;             // (V,H) fp32, accumulated with atomics (caller zero-fills)
   float* db;             // (V) fp32, accumulated with atomics (column sums of g, taken from the A stages)
   const float* gscale;   // {S, 1/S}
@@ -93,13 +93,14 @@ int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream);
 
 size_t joint_gemm_smem_bytes();
 int joint_gemm_scratch_tiles(int grid);   // tiles of per-CTA activation scratch the forward needs when h_map == 2
-// tmW: 64(k) x 128(v) boxes (each CTA of a pair loads half of a 256-class block); max_tiles bounds the work list
-int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const JointArgs& args,
-                      long long max_tiles, cudaStream_t stream);
-// tmG: 64(v) x 128(cell) boxes of the gradient ring; chunk_tiles bounds the work-list slots of this ring chunk
-int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, long long chunk_tiles,
+// tmW: 64(k) x 128(v) boxes (each CTA of a pair loads half of a 256-class block); tmH / tmH2: 64(k) x 64 / 128 (row)
+// boxes of the activation buffer (one half-tile / two adjacent ones); max_slots bounds the work-list slots of this launch
+int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const CUtensorMap& tmH2,
+                      const JointArgs& args, long long max_slots, cudaStream_t stream);
+// tmG: 64(v) x 128(cell) boxes of the gradient ring; chunk_slots bounds the work-list slots of this ring chunk
+int launch_dh_gemm(const CUtensorMap& tmG, const CUtensorMap& tmWmn, const DhArgs& args, long long chunk_slots,
                    cudaStream_t stream);
-int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, long long chunk_tiles,
+int launch_dw_gemm(const CUtensorMap& tmGmn, const CUtensorMap& tmHmn, const DwArgs& args, long long chunk_slots,
                    cudaStream_t stream);   // picks args.ksplit itself
 
 // prep / small kernels (prep.cu, lattice.cu, decode.cu)
@@ -112,8 +113,9 @@ int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, i
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
                 const float* gscale, const int* T_len, const int* U_len, int B, int T, int U1, float4* coef,
                 cudaStream_t stream);
+// flags / sub_list are indexed by half-tile (2 per lattice tile)
 int launch_tile_activity(const float4* coef, const int* T_len, const int* U_len, const int* tile_off, int B, int T,
-                         int U1, long long max_tiles, int dense, unsigned char* flags, int* tile_list, int* n_active,
+                         int U1, long long max_tiles, int dense, unsigned char* flags, int* sub_list, int* n_active,
                          cudaStream_t stream);
 int launch_dense_logprobs(const float* logits, const int* targets, int tgt_ld, const int* T_len, const int* U_len,
                           int B, int T, int U1, int V, int blank, float* lp, float* lse, cudaStream_t stream);

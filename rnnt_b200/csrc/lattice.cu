@@ -188,37 +188,44 @@ __global__ void coef_kernel(const float* __restrict__ lp, const float* __restric
 
 // ---- occupancy sparsity of the backward.  The logit-gradients of a cell are bounded by max(|gamma'|,|eB'|,|eE'|)
 // (coef already carries dcost * S); below 2^-25 every fp16 value stored in the gradient ring would round to zero, so
-// a tile whose 128 cells are all below that bound contributes exactly nothing to dh / dW / db and is dropped from
-// the backward's tile list.  One warp per tile, then a single-block compaction (order preserved).
+// a HALF-TILE (16 t x 4 u = 64 cells) whose cells are all below that bound contributes exactly nothing to
+// dh / dW / db and is dropped from the backward's work list.  One warp per half-tile, then a single-block compaction
+// (order preserved).  In dense mode every half-tile that holds at least one valid cell stays.
 __global__ void tile_activity_kernel(const float4* __restrict__ coef, const int* __restrict__ T_len,
                                      const int* __restrict__ U_len, const int* __restrict__ tile_off, int B, int T,
                                      int U1, int dense, unsigned char* __restrict__ flags) {
-  const int total = __ldg(tile_off + B);
+  const int total = 2 * __ldg(tile_off + B);
   const int lane = threadIdx.x & 31;
   const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int tile = w0; tile < total; tile += nw) {
-    const TileCoord tc = decode_tile(tile_off, T_len, U_len, B, tile);
+  for (int hid = w0; hid < total; hid += nw) {
+    const TileCoord tc = decode_half(tile_off, T_len, U_len, B, hid);
     float mx = 0.f;
+    int any_valid = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = lane * 4 + i;
-      const int t = tc.t0 + (r >> 3), u = tc.u0 + (r & 7);
+    for (int i = 0; i < 2; ++i) {
+      const int r = lane * 2 + i;
+      const int t = tc.t0 + (r >> 2), u = tc.u0 + (r & 3);
       if (t < tc.Tb && u <= tc.Ub) {
         const float4 c = __ldg(coef + (static_cast<long long>(tc.b) * T + t) * U1 + u);
         mx = fmaxf(mx, fmaxf(fabsf(c.x), fmaxf(fabsf(c.y), fabsf(c.z))));
+        if (!(c.x == c.x) || !(c.y == c.y) || !(c.z == c.z)) mx = INFINITY;   // NaN stays active
+        any_valid = 1;
       }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) flags[tile] = (dense || mx > 2.98023224e-8f || !(mx == mx)) ? 1 : 0;   // 2^-25; NaN stays active
+    for (int o = 16; o; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      any_valid |= __shfl_xor_sync(0xffffffffu, any_valid, o);
+    }
+    if (lane == 0) flags[hid] = (any_valid && (dense || mx > 2.98023224e-8f)) ? 1 : 0;   // 2^-25
   }
 }
 
 __global__ void tile_compact_kernel(const unsigned char* __restrict__ flags, const int* __restrict__ tile_off, int B,
-                                    int* __restrict__ tile_list, int* __restrict__ n_active) {
+                                    int* __restrict__ sub_list, int* __restrict__ n_active) {
   __shared__ int sums[1024];
-  const int total = __ldg(tile_off + B);
+  const int total = 2 * __ldg(tile_off + B);
   const int per = (total + blockDim.x - 1) / blockDim.x;
   const int lo = min(total, (int)threadIdx.x * per), hi = min(total, lo + per);
   int cnt = 0;
@@ -233,7 +240,7 @@ __global__ void tile_compact_kernel(const unsigned char* __restrict__ flags, con
   }
   int pos = sums[threadIdx.x] - cnt;
   for (int i = lo; i < hi; ++i)
-    if (flags[i]) tile_list[pos++] = i;
+    if (flags[i]) sub_list[pos++] = i;
   if (threadIdx.x == blockDim.x - 1) *n_active = sums[threadIdx.x];
 }
 
@@ -346,12 +353,12 @@ int launch_coef(const float* lp, const float* lse, const float* alpha, const flo
 }
 
 int launch_tile_activity(const float4* coef, const int* T_len, const int* U_len, const int* tile_off, int B, int T,
-                         int U1, long long max_tiles, int dense, unsigned char* flags, int* tile_list, int* n_active,
+                         int U1, long long max_tiles, int dense, unsigned char* flags, int* sub_list, int* n_active,
                          cudaStream_t stream) {
   ProfScope prof_(kProfPrep, stream);
-  const int grid = static_cast<int>(std::min<long long>((max_tiles + 7) / 8, 148 * 8));
+  const int grid = static_cast<int>(std::min<long long>((2 * max_tiles + 7) / 8, 148 * 8));
   tile_activity_kernel<<<grid, 256, 0, stream>>>(coef, T_len, U_len, tile_off, B, T, U1, dense, flags);
-  tile_compact_kernel<<<1, 1024, 0, stream>>>(flags, tile_off, B, tile_list, n_active);
+  tile_compact_kernel<<<1, 1024, 0, stream>>>(flags, tile_off, B, sub_list, n_active);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -27,11 +27,11 @@ _last_decode_phase_cycles = None   # int64[8] cycle counters of the last decode 
 
 
 def last_backward_stats():
-    """(active_tiles, total_tiles) of the most recent fused backward, or None.  Synchronises."""
+    """(active, total) half-tiles (16 t x 4 u lattice blocks) of the most recent fused backward, or None.  Synchronises."""
     if _last_backward_stats is None:
         return None
     a, t = _last_backward_stats.tolist()
-    return int(a), int(t)
+    return int(a), 2 * int(t)
 
 
 def _stream_ptr(device) -> int:

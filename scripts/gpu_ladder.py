@@ -65,7 +65,7 @@ def _fwd_bwd(B, T, U, H, V, ragged, ring_tiles=None, check_rings=True):
         g_ring, h_ring, S = ring_views(out)
         print('  gradient scale S =', S)
         rows = tile_rows(inp["T_len"], inp["U_len"], out)
-        print("  active tiles", out["active_tiles"], "of", out["total_tiles"])
+        print("  active half-tiles", out["active_halves"], "of", out["total_halves"])
         n = min(len(rows), g_ring.shape[0])
         bi = torch.tensor([r[0] for r in rows[:n]], device="cuda")
         ti = torch.tensor([min(r[1], T - 1) for r in rows[:n]], device="cuda")

@@ -114,7 +114,7 @@ def test_recompute_mode_equals_saved_activation_mode():
 
 
 def test_saved_activations_are_the_fp16_tanh():
-    """The residual buffer holds h = tanh(enc+pred) in fp16, one 128-row block per 16(t) x 8(u) lattice tile."""
+    """The residual buffer holds h = tanh(enc+pred) in fp16, one 64-row block per 16(t) x 4(u) half-tile."""
     from helpers import tile_rows
     inp = make_inputs(2, 21, 9, 64, 256, ragged=True, seed=5)
     out = fused_raw(inp)
@@ -133,8 +133,8 @@ def test_zero_tile_skipping_is_exact():
     inp = make_inputs(2, 160, 40, 128, 512, ragged=True, seed=17)
     dense = fused_raw(inp, flags=1)
     sparse = fused_raw(inp, flags=0)
-    assert dense["active_tiles"] == dense["total_tiles"]
-    assert 0 < sparse["active_tiles"] < sparse["total_tiles"]
+    assert dense["total_halves"] // 2 < dense["active_halves"] <= dense["total_halves"]   # all halves holding a valid cell
+    assert 0 < sparse["active_halves"] < dense["active_halves"]
     for k in ("d_enc", "d_pred", "dW", "db"):
         assert rel_err(sparse[k], dense[k])[0] < 2e-6, (k, rel_err(sparse[k], dense[k]))
     ref = torch_reference(inp)
