@@ -24,7 +24,7 @@ namespace {
 constexpr int kStages = 6;
 constexpr int kBytesA = kBK * 128 * 2;          // 16 KB: 64 v x 128 k (this CTA's hidden units)
 constexpr int kBytesB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's 128 of the item's 256 cells x 64 v
-constexpr int kEpiSets = 4;                       // epilogue warp sets; set e handles lattice tile e of the item
+constexpr int kEpiSets = 2;                       // epilogue warp sets; set e handles lattice tile e of the item
 constexpr int kNumThreads = 64 + 128 * kEpiSets;
 constexpr int kTmemCols = 512;
 
