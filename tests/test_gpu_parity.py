@@ -97,7 +97,7 @@ def test_recompute_mode_equals_saved_activation_mode():
         assert torch.equal(saved["costs"], lean["costs"])
         assert torch.equal(saved["lp"], lean["lp"])
         for k in ("d_enc", "d_pred", "dW", "db"):
-            assert rel_err(lean[k], saved[k])[0] < 2e-6, (shape, k, rel_err(lean[k], saved[k]))
+            assert rel_err(lean[k], saved[k])[0] < 1e-5, (shape, k, rel_err(lean[k], saved[k]))
     # public API: loss-only evaluation (no grad -> no residual buffer) and the save_hidden switch
     inp = make_inputs(2, 40, 20, 256, 1024, ragged=True, seed=11)
     args = (inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"])
@@ -110,7 +110,7 @@ def test_recompute_mode_equals_saved_activation_mode():
         assert torch.equal(costs.detach(), plain)
         costs.sum().backward()
         grads.append(enc.grad)
-    assert rel_err(grads[1], grads[0])[0] < 2e-6
+    assert rel_err(grads[1], grads[0])[0] < 1e-5
 
 
 def test_saved_activations_are_the_fp16_tanh():
@@ -136,7 +136,7 @@ def test_zero_tile_skipping_is_exact():
     assert dense["total_halves"] // 2 < dense["active_halves"] <= dense["total_halves"]   # all halves holding a valid cell
     assert 0 < sparse["active_halves"] < dense["active_halves"]
     for k in ("d_enc", "d_pred", "dW", "db"):
-        assert rel_err(sparse[k], dense[k])[0] < 2e-6, (k, rel_err(sparse[k], dense[k]))
+        assert rel_err(sparse[k], dense[k])[0] < 1e-5, (k, rel_err(sparse[k], dense[k]))
     ref = torch_reference(inp)
     for k in ("d_enc", "d_pred", "dW", "db"):
         assert rel_err(sparse[k], ref[k])[0] <= GRAD_TOL_FP32, k
