@@ -80,51 +80,61 @@ template <bool BETA>
 __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, float* __restrict__ out,
                                              float* __restrict__ costs_b, int Tb, int Ub, int U1, int u, float* sh0,
                                              float* sh1) {
+  // The step time of this kernel is (instructions per step) x (dependent-issue latency): one warp per scheduler, no
+  // other work to hide behind.  So everything that is not the recursion itself is hoisted out of the step: the
+  // activity test is one unsigned compare, the store walks a pointer, the emit log-prob of the last column is -inf
+  // already when it is fetched, and the corner cell needs no special case (own = 0, side = -inf gives LSE = 0 / lpB).
   const int ndiag = Tb + Ub;
   const bool col_ok = u <= Ub;
-  const int s0 = BETA ? (Ub - u) : u;                       // first active step of this thread
+  const int s0 = col_ok ? (BETA ? (Ub - u) : u) : 0x40000000;   // first active step (never, for columns past Ub)
   const long long step = BETA ? -static_cast<long long>(U1) : U1;
-  const long long first = (BETA ? static_cast<long long>(Tb - 1) * U1 : 0) + u;
+  const long long first = (BETA ? static_cast<long long>(Tb - 1) * U1 : 0) + min(u, U1 - 1);
   const float2* src = lp2 + first;                           // cell visited at local step 0
-  float* dst = out + first;
+  float* dptr = out + first;
   const int nb = BETA ? u + 1 : u - 1;                       // neighbour column feeding this one
+  const bool last_col = u >= Ub;
 
   float2 cur[kPre], nxt[kPre];
   auto fetch = [&](int g, float2 (&d)[kPre]) {
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
       const int rel = g * kPre + i - s0;
-      d[i] = (col_ok && rel >= 0 && rel < Tb) ? __ldg(src + rel * step) : make_float2(0.f, 0.f);
+      float2 v = make_float2(0.f, 0.f);
+      if (static_cast<unsigned>(rel) < static_cast<unsigned>(Tb)) v = __ldg(src + rel * step);
+      if (last_col) v.y = -INFINITY;                         // no emission out of the last column
+      d[i] = v;
     }
   };
   const int ngroups = (ndiag + kPre - 1) / kPre;
   fetch(0, cur);
-  float own = -INFINITY;   // alpha: alpha(t-1,u)+lpB(t-1,u);  beta: beta(t+1,u)
+  // alpha: own = alpha(t-1,u)+lpB(t-1,u);  beta: own = beta(t+1,u).  The corner cell starts from own = 0.
+  float own = ((BETA ? u == Ub : u == 0)) ? 0.f : -INFINITY;
+  float last = 0.f;
   for (int g = 0; g < ngroups; ++g) {
     if (g + 1 < ngroups) fetch(g + 1, nxt);
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
       const int s = g * kPre + i;
       if (s < ndiag) {    // uniform over the block
-        const int rel = s - s0;
-        float* wr = (s & 1) ? sh1 : sh0;
-        const float* rd = (s & 1) ? sh0 : sh1;
+        float* wr = (i & 1) ? sh1 : sh0;                     // kPre is even: the parity of s is the parity of i
+        const float* rd = (i & 1) ? sh0 : sh1;
         float pub = -INFINITY;
-        if (col_ok && rel >= 0 && rel < Tb) {
+        if (static_cast<unsigned>(s - s0) < static_cast<unsigned>(Tb)) {
           const float lpB = cur[i].x, lpE = cur[i].y;
           const float side = rd[nb];                     // guards hold -inf at columns -1 and blockDim.x
-          float val;
           if (!BETA) {
-            val = (s == 0) ? 0.f : lse2f(own, side);     // own = -inf at t = 0, side = -inf at u = 0
+            const float val = lse2f(own, side);          // own = -inf at t = 0, side = -inf at u = 0
             own = val + lpB;                             // feeds alpha(t+1,u)
-            pub = (u < Ub) ? val + lpE : -INFINITY;      // feeds alpha(t,u+1)
+            pub = val + lpE;                             // feeds alpha(t,u+1); -inf out of the last column
+            *dptr = val;
           } else {
-            val = (s == 0) ? lpB : lse2f(own + lpB, (u < Ub) ? side + lpE : -INFINITY);   // own = -inf at t = Tb-1
+            const float val = lse2f(own + lpB, side + lpE);   // own = -inf at t = Tb-1 except in the corner
             own = val;
             pub = val;
-            if (s == ndiag - 1) *costs_b = -val;
+            last = val;
+            *dptr = val;
           }
-          dst[rel * step] = val;
+          dptr += step;
         }
         wr[u] = pub;
         __syncthreads();
@@ -133,6 +143,7 @@ __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, flo
 #pragma unroll
     for (int i = 0; i < kPre; ++i) cur[i] = nxt[i];
   }
+  if (BETA && u == 0) *costs_b = -last;                  // beta(0,0) is the last cell column 0 visits
 }
 
 __global__ void lattice_kernel(const float* __restrict__ lp, const int* __restrict__ T_len,
