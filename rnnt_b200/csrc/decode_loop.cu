@@ -111,12 +111,15 @@ template <bool GELU, int OUT>
 __device__ void batched_gemv(const float* __restrict__ W, const float* __restrict__ bias, int nout, int klen,
                              const Seg* segs, int nsegs, const int* __restrict__ rows, int nrows,
                              float* __restrict__ out, long long out_stride, float* smem, int smem_floats,
-                             float* partial) {
+                             float* partial, int rsplit = 1) {
   static_assert(OUT * kRows == 32 || OUT * kRows == 64, "partial sums per thread must be 32 or 64");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k4 = klen >> 2;
-  const int ntasks = (nout + OUT - 1) / OUT;
-  const int nchunks = (nrows + kRows - 1) / kRows;
+  // a task = OUT outputs x one of `rsplit` ranges of row chunks (more tasks than SMs would cost a second wave, fewer
+  // leave SMs idle: the callers pick OUT and rsplit so that ntasks is just under the grid size)
+  const int ntasks = ((nout + OUT - 1) / OUT) * rsplit;
+  const int nchunks_all = (nrows + kRows - 1) / kRows;
+  const int chunks_per_part = (nchunks_all + rsplit - 1) / rsplit;
   const int depth = max(2, min(4, smem_floats / (kRows * klen)));   // staging ring: chunks c .. c+depth-1 in flight
 
   auto stage = [&](int chunk, float* dst) {
@@ -134,13 +137,16 @@ __device__ void batched_gemv(const float* __restrict__ W, const float* __restric
   };
 
   for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    const int o0 = task * OUT;
+    const int o0 = (task / rsplit) * OUT;
+    const int c_lo = (task % rsplit) * chunks_per_part;
+    const int nchunks = min(nchunks_all, c_lo + chunks_per_part) - c_lo;   // chunks c_lo .. c_lo + nchunks - 1
+    if (nchunks <= 0) continue;         // uniform over the CTA
     const float4* w4[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) w4[o] = reinterpret_cast<const float4*>(W + static_cast<long long>(min(o0 + o, nout - 1)) * klen);
     __syncthreads();                    // previous users of the staging buffers are done
     for (int c = 0; c < depth - 1; ++c) {
-      if (c < nchunks) stage(c, smem + (c % depth) * kRows * klen); else cp_async_commit();
+      if (c < nchunks) stage(c_lo + c, smem + (c % depth) * kRows * klen); else cp_async_commit();
     }
     // this thread's slice of the OUT weight rows stays in registers for the whole task (K <= 3072)
     float4 wreg[kMaxIt][OUT];
@@ -151,9 +157,9 @@ __device__ void batched_gemv(const float* __restrict__ W, const float* __restric
       for (int o = 0; o < OUT; ++o) wreg[it][o] = (i < k4) ? __ldg(w4[o] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int c = 0; c < nchunks; ++c) {
-      const int r0 = c * kRows, nr = min(kRows, nrows - r0);
+      const int r0 = (c_lo + c) * kRows, nr = min(kRows, nrows - r0);
       const int ahead = c + depth - 1;    // one commit per iteration keeps the group count uniform
-      if (ahead < nchunks) stage(ahead, smem + (ahead % depth) * kRows * klen); else cp_async_commit();
+      if (ahead < nchunks) stage(c_lo + ahead, smem + (ahead % depth) * kRows * klen); else cp_async_commit();
       cp_async_wait_pending(depth - 1);
       __syncthreads();                  // chunk c has landed for every thread
       const float4* x4 = reinterpret_cast<const float4*>(smem + (c % depth) * kRows * klen);
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
       // ---- P4: conv1 at the new position: [xs(b,0), xs(b,1), xnew(b)] . w1^T
       {
         Seg segs[2] = {{p.xs, 2LL * E, 2 * E}, {p.xnew, E, E}};
-        batched_gemv<true, 4>(p.w1, p.b1, E, 3 * E, segs, 2, rows_emit, n_emit, p.ynew, E, smem, p.smem_floats, partial);
+        batched_gemv<true, 8>(p.w1, p.b1, E, 3 * E, segs, 2, rows_emit, n_emit, p.ynew, E, smem, p.smem_floats, partial, p.rsplit_e);
       }
       lap(3);
       grid.sync();
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
       // ---- P5: conv2 at the new position: [ys(b,0..3), ynew(b)] . w2^T ; conv1 state shifts (xs is no longer read)
       {
         Seg segs[2] = {{p.ys, 4LL * E, 4 * E}, {p.ynew, E, E}};
-        batched_gemv<true, 4>(p.w2, p.b2, E, 5 * E, segs, 2, rows_emit, n_emit, p.z, E, smem, p.smem_floats, partial);
+        batched_gemv<true, 8>(p.w2, p.b2, E, 5 * E, segs, 2, rows_emit, n_emit, p.z, E, smem, p.smem_floats, partial, p.rsplit_e);
       }
       for (int j = blockIdx.x; j < n_emit; j += gridDim.x) {
         const int b = rows_emit[j];
@@ -395,6 +401,8 @@ int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream) {
   const size_t smem_min = 2 * static_cast<size_t>(kRows) * klen_max * sizeof(float);   // at least double-buffered staging
   const size_t smem = std::max<size_t>(smem_min, 192 * 1024);   // deeper ring (up to 4 chunks) for the narrower phases
   a.smem_floats = static_cast<int>(smem / sizeof(float));
+  // conv phases: E/8 output blocks x rsplit row ranges should just fill the grid (E=512: 64 x 2 = 128 tasks on 148 SMs)
+  a.rsplit_e = std::max(1, std::min(4, device_sm_count() / std::max(1, (a.E + 7) / 8)));
   RB_REQUIRE(smem <= 200 * 1024 && klen_max <= 4 * kMaxIt * kThreads, -6,
              "decode kernel supports hidden_features <= 3072 and embedding dim <= 614");
   // carve the scratch

@@ -79,7 +79,7 @@ struct DecodeArgs {
   const float* w2; const float* b2;                       // conv2 as (E, 5E)
   const float* wl; const float* bl;                       // linear (H,E), (H)
   const float* ln2_w; const float* ln2_b;                 // output LayerNorm (H)
-  int B, T, H, V, E, blank, max_len, max_per_frame, max_steps, smem_floats;
+  int B, T, H, V, E, blank, max_len, max_per_frame, max_steps, smem_floats, rsplit_e;
   int* tokens;             // (B, max_len) emitted tokens (seed blank excluded)
   int* ntok;               // (B) 1 + number of emitted tokens
   // scratch (carved by the launcher)
