@@ -204,6 +204,29 @@ def other_configs(torch, dev):
                     peak_mem_gib=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
 
     out = {}
+    # context only: the ops the reference's call path launches on a GPU (cuBLAS fp32 linear + tanh + torchaudio's
+    # CUDA rnnt_loss, materialised logits), timed on this GPU at a batch that fits
+    try:
+        import torchaudio
+        ri = synth_inputs(torch, 4242, dev, b=8)
+        for k in ("enc", "pred", "W", "b"):
+            ri[k].requires_grad_(True)
+
+        def ref_gpu_step():
+            for k in ("enc", "pred", "W", "b"):
+                ri[k].grad = None
+            hid = torch.tanh(ri["enc"].unsqueeze(2) + ri["pred"].unsqueeze(1))
+            logits = torch.nn.functional.linear(hid, ri["W"], ri["b"])
+            torchaudio.functional.rnnt_loss(logits, ri["targets"], ri["T_len"], ri["U_len"], blank=-1, clamp=-1,
+                                            reduction="mean").backward()
+        ms = timed(ref_gpu_step, 3)
+        out["reference_ops_on_this_gpu_B8_T400_U100_V1024"] = dict(
+            ms_per_step=ms, value=8 * T * (U + 1) / (ms * 1e-3), unit=UNIT,
+            note="torch fp32 linear + tanh + torchaudio CUDA rnnt_loss fwd+bwd; context, not the contract's reference arm")
+        del ri
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        out["reference_ops_on_this_gpu_B8_T400_U100_V1024"] = dict(error=repr(exc))
     out["cpu_reference_shape_B4_T200_U40_V1024"] = loss_cfg(4, 200, 40, 1024, False, 20)
     out["ragged_B32_T400_U100_V1024"] = loss_cfg(32, 400, 100, 1024, True, 5)
     out["stress_B8_T1500_U300_V4096_ragged"] = loss_cfg(8, 1500, 300, 4096, True, 2)
