@@ -32,12 +32,12 @@ extern "C" {
 int rnnt_b200_abi_version(void);
 const char* rnnt_b200_last_error(void);
 
-/* Upper bound on the number of 16(t) x 8(u) lattice tiles of a (B,T,U1) batch. */
+/* Upper bound on the number of 128-row GEMM units (= pairs of 16(t) x 4(u) half-tiles) of a (B,T,U1) batch. */
 int64_t rnnt_b200_max_tiles(int B, int T, int U1);
 
-/* Size in bytes of the optional activation residual `hidden`: h = tanh(enc + pred) as fp16, one 128-row block per
- * 16(t) x 8(u) lattice tile stored as two 16 x 4 half-tiles of 64 rows (row r of a half = cell (t0 + r/4,
- * u0 + 4*half + r%4)), rows padded to a multiple of 64 hidden units.  The reference's autograd saves the same tensor in fp32
+/* Size in bytes of the optional activation residual `hidden`: h = tanh(enc + pred) as fp16, one 64-row block per
+ * half-tile of 16(t) x 4(u) lattice cells (row r = cell (t0 + r/4, u0 + r%4); half-tiles are numbered utterance by
+ * utterance, t-block by t-block, u-block by u-block), rows padded to a multiple of 64 hidden units.  The reference's autograd saves the same tensor in fp32
  * (rnnt/joint.py:37).  With it the backward does not recompute the tanh; without it (NULL) it does. */
 size_t rnnt_b200_hidden_bytes(int B, int T, int U1, int H);
 
@@ -124,12 +124,12 @@ int rnnt_b200_profile_begin(void);
 int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
 
 /* Test hook: byte offsets of the workspace regions so tests can inspect the rings after a backward call:
- *   offsets[0] tile table: B+1 int32 prefix sums of tiles per utterance, status, {S, 1/S} (fp32), n_active half-tiles
+ *   offsets[0] tile table: B+1 int32 prefix sums of half-tiles per utterance, status, {S, 1/S} (fp32), n_active half-tiles
  *   offsets[1] W as fp16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
  *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] fp16
  *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16 (-1 with have_hidden)
  *   offsets[6] bytes that satisfy both the forward and the backward call
- *   offsets[7] work list of active half-tiles (int32 ids = 2 * tile + half); ring rows [64 i, 64 i + 64) = entry i.
+ *   offsets[7] work list of active half-tiles (int32 ids); ring rows [64 i, 64 i + 64) = entry i.
  * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
 int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
                               int64_t* offsets /*[8]*/, int* Hp, int* Vp);

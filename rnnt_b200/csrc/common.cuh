@@ -14,9 +14,11 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 // ---------------------------------------------------------------------------------------------
 // Tile geometry shared by every kernel of the path (see DESIGN.md "Tile map").
-// A tile is a 16(t) x 8(u) block of one utterance's lattice = 128 GEMM rows, stored as two HALF-TILES of 16(t) x 4(u)
-// = 64 rows each (row r of a half <-> (t0 + (r>>2), u0 + 4*half + (r&3))).  Half-tile id = 2 * tile + half.  The
-// backward's work list, the gradient ring and the activation buffer are all organised in half-tiles.
+// The lattice of every utterance is cut into HALF-TILES of 16(t) x 4(u) cells = 64 GEMM rows (row r <-> (t0 + (r>>2),
+// u0 + (r&3))), numbered utterance by utterance, t-block by t-block, u-block by u-block; tile_off[b] is the number of
+// half-tiles before utterance b.  A GEMM unit (128 rows, one CTA) is two half-tiles: consecutive ids in the forward,
+// any two entries of the active list in the backward.  The activation buffer, the gradient ring and the work list are
+// all organised in half-tiles.
 constexpr int kTileT = 16;
 constexpr int kTileU = 8;
 constexpr int kTileM = 128;
@@ -264,24 +266,17 @@ __device__ __forceinline__ int find_utt(const int* __restrict__ tile_off, int B,
 struct TileCoord {
   int b, t0, u0, Tb, Ub;
 };
-__device__ __forceinline__ TileCoord decode_tile(const int* __restrict__ tile_off, const int* __restrict__ T_len,
-                                                 const int* __restrict__ U_len, int B, int tile) {
-  TileCoord c;
-  c.b = find_utt(tile_off, B, tile);
-  c.Tb = __ldg(T_len + c.b);
-  c.Ub = __ldg(U_len + c.b);
-  int nu = (c.Ub + 1 + kTileU - 1) / kTileU;
-  int local = tile - __ldg(tile_off + c.b);
-  c.t0 = (local / nu) * kTileT;
-  c.u0 = (local % nu) * kTileU;
-  return c;
-}
-
-// half-tile id -> coordinates; u0 is the first column of the HALF (tile u0 + 4 * half)
+// half-tile id -> utterance, first frame t0, first label position u0, and the utterance's lengths
 __device__ __forceinline__ TileCoord decode_half(const int* __restrict__ tile_off, const int* __restrict__ T_len,
                                                  const int* __restrict__ U_len, int B, int half_id) {
-  TileCoord c = decode_tile(tile_off, T_len, U_len, B, half_id >> 1);
-  c.u0 += (half_id & 1) * kHalfU;
+  TileCoord c;
+  c.b = find_utt(tile_off, B, half_id);
+  c.Tb = __ldg(T_len + c.b);
+  c.Ub = __ldg(U_len + c.b);
+  const int nu = (c.Ub + 1 + kHalfU - 1) / kHalfU;
+  const int local = half_id - __ldg(tile_off + c.b);
+  c.t0 = (local / nu) * kTileT;
+  c.u0 = (local % nu) * kHalfU;
   return c;
 }
 

@@ -98,7 +98,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
 
   // work list: slots of 64 rows (half-tiles); identity over all half-tiles in the forward
-  const int total_slots = p.n_active ? __ldg(p.n_active) : 2 * __ldg(p.tile_off + p.B);
+  const int total_slots = p.n_active ? __ldg(p.n_active) : __ldg(p.tile_off + p.B);
   const int slot_end = min(total_slots, p.slot_begin + p.slot_cap);   // this launch: slots [slot_begin, slot_end)
   const int nunits = (max(0, slot_end - p.slot_begin) + 1) >> 1;      // 128-row units = pairs of consecutive slots
   const int nk = p.Hp / kBK;

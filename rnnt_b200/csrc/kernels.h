@@ -21,7 +21,7 @@ struct JointArgs {
   int tgt_ld;
   const int* T_len;
   const int* U_len;
-  const int* tile_off;    // [B+1] prefix sum of tiles per utterance; tile_off[B] = total
+  const int* tile_off;    // [B+1] prefix sum of half-tiles (16 t x 4 u) per utterance; tile_off[B] = total
   int B, T, U1, H, Hp, V, Vp, blank;
   int slot_begin, slot_cap;   // process work-list slots (half-tiles, 64 rows) [slot_begin, min(count, slot_begin + slot_cap))
   const int* sub_list;    // G: slot -> half-tile id (active ones only); nullptr (F) = identity over all half-tiles

@@ -44,7 +44,7 @@ __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __re
     if (Tb < 1 || Tb > T || Ub < 0 || Ub > U1 - 1) bad = 1;
     Tb = max(1, min(Tb, T));
     Ub = max(0, min(Ub, U1 - 1));
-    acc += ((Tb + kTileT - 1) / kTileT) * ((Ub + 1 + kTileU - 1) / kTileU);
+    acc += ((Tb + kTileT - 1) / kTileT) * ((Ub + 1 + kHalfU - 1) / kHalfU);     // half-tiles of 16(t) x 4(u)
     tile_off[b + 1] = acc;
   }
   if (err_flag) *err_flag = bad;
@@ -205,7 +205,7 @@ __global__ void coef_kernel(const float* __restrict__ lp, const float* __restric
 __global__ void tile_activity_kernel(const float4* __restrict__ coef, const int* __restrict__ T_len,
                                      const int* __restrict__ U_len, const int* __restrict__ tile_off, int B, int T,
                                      int U1, int dense, unsigned char* __restrict__ flags) {
-  const int total = 2 * __ldg(tile_off + B);
+  const int total = __ldg(tile_off + B);
   const int lane = threadIdx.x & 31;
   const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -236,7 +236,7 @@ __global__ void tile_activity_kernel(const float4* __restrict__ coef, const int*
 __global__ void tile_compact_kernel(const unsigned char* __restrict__ flags, const int* __restrict__ tile_off, int B,
                                     int* __restrict__ sub_list, int* __restrict__ n_active) {
   __shared__ int sums[1024];
-  const int total = 2 * __ldg(tile_off + B);
+  const int total = __ldg(tile_off + B);
   const int per = (total + blockDim.x - 1) / blockDim.x;
   const int lo = min(total, (int)threadIdx.x * per), hi = min(total, lo + per);
   int cnt = 0;

@@ -31,7 +31,7 @@ def last_backward_stats():
     if _last_backward_stats is None:
         return None
     a, t = _last_backward_stats.tolist()
-    return int(a), 2 * int(t)
+    return int(a), int(t)
 
 
 def _stream_ptr(device) -> int:

@@ -70,8 +70,7 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0, save_hidden
     torch.cuda.synchronize()
     meta = ws[int(offs[0]): int(offs[0]) + (B + 5) * 4].view(torch.int32)
     out.update(ws=ws, hidden=hidden, offs=[int(x) for x in offs], Hp=hp.value, Vp=vp.value, ring_tiles=ring_tiles,
-               status=int(status.item()), total_tiles=int(meta[B]), total_halves=2 * int(meta[B]),
-               active_halves=int(meta[B + 4]))
+               status=int(status.item()), total_halves=int(meta[B]), active_halves=int(meta[B + 4]))
     return out
 
 
@@ -90,9 +89,10 @@ def ring_views(out):
 
 
 def tile_rows(T_len, U_len, out=None):
-    """(b, t, u, valid) for every row of the activation buffer (half-tile order: 16(t) x 8(u) tiles, each stored as two
-    16(t) x 4(u) halves of 64 rows, row r of a half <-> (t0 + r//4, u0 + 4*half + r%4)).  Mirrors the kernels' tile map;
-    with `out` (result of fused_raw) only the half-tiles of the backward's work list are returned, in ring order."""
+    """(b, t, u, valid) for every row of the activation buffer: the lattice of each utterance is cut into half-tiles of
+    16(t) x 4(u) cells = 64 rows (row r <-> (t0 + r//4, u0 + r%4)), enumerated utterance by utterance, t-block by
+    t-block, u-block by u-block.  Mirrors the kernels' map; with `out` (result of fused_raw) only the half-tiles of the
+    backward's work list are returned, in ring order."""
     rows = []
     if out is not None:
         n = out["active_halves"]
@@ -102,13 +102,12 @@ def tile_rows(T_len, U_len, out=None):
             rows.extend(allrows[hid * 64:(hid + 1) * 64])
         return rows
     for b, (Tb, Ub) in enumerate(zip(T_len.tolist(), U_len.tolist())):
-        nt, nu = (Tb + 15) // 16, (Ub + 1 + 7) // 8
+        nt, nu = (Tb + 15) // 16, (Ub + 1 + 3) // 4
         for it in range(nt):
             for iu in range(nu):
-                for half in range(2):
-                    for r in range(64):
-                        t, u = it * 16 + (r >> 2), iu * 8 + 4 * half + (r & 3)
-                        rows.append((b, t, u, t < Tb and u <= Ub))
+                for r in range(64):
+                    t, u = it * 16 + (r >> 2), iu * 4 + (r & 3)
+                    rows.append((b, t, u, t < Tb and u <= Ub))
     return rows
 
 
