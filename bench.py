@@ -318,7 +318,7 @@ def run_gpu_arm(args):
     _lib.check(L.rnnt_b200_profile_end(fam_ms, fam_n), "profile_end")
     clocks = sampler.stop() if rank == 0 else None
     loss_val = float(last.detach())
-    # secondary number: the same step with the backward forced over ALL lattice tiles (no zero-tile skipping)
+    # secondary number: the same step with the backward forced over ALL half-tiles of the lattice (no zero-gradient skipping)
     dense_ms = None
     if not args.all_tiles:
         args.all_tiles = True
@@ -410,7 +410,7 @@ def run_gpu_arm(args):
             kern[nm] = dict(ms_per_step=per_step_ms, launches_per_step=fam_n[i] / args.steps,
                             share=per_step_ms / ms_step)
             if nm in ("joint_gemm_fwd", "joint_gemm_bwd", "dh_gemm", "dw_gemm"):
-                # executed algorithmic FLOPs: the backward GEMMs only run over lattice tiles with non-zero gradients
+                # executed algorithmic FLOPs: the backward GEMMs only run over half-tiles with non-zero gradients
                 frac = 1.0 if nm == "joint_gemm_fwd" else bwd_frac
                 kern[nm]["flops_per_step"] = gemm_flops_per_step_rank * frac
                 kern[nm]["tflops"] = gemm_flops_per_step_rank * frac / (per_step_ms * 1e-3) / 1e12
@@ -467,7 +467,7 @@ def run_gpu_arm(args):
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(sum(fam_n)),
                     all_tiles=(dict(ms_per_step=dense_ms, value=cells_step / (dense_ms * 1e-3), unit=UNIT,
-                                    note="same step, backward over every lattice tile (zero-gradient tiles not skipped)")
+                                    note="same step, backward over every half-tile of the lattice (zero-gradient ones not skipped)")
                                if dense_ms else None),
                     roofline=roofline)
         if cpu_base is not None:
@@ -489,7 +489,7 @@ def main():
     ap.add_argument("--no-kernel-profile", action="store_true", help="skip the per-kernel CUDA events")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
     ap.add_argument("--all-tiles", action="store_true",
-                    help="backward processes every lattice tile (also those whose fp16 gradients are all zero)")
+                    help="backward processes every half-tile of the lattice (also those whose fp16 gradients are all zero)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

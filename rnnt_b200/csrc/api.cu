@@ -129,7 +129,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
 
   const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
-  // activation rows h = tanh(enc+pred): the caller's residual buffer (one 128-row block per lattice tile) or a
+  // activation rows h = tanh(enc+pred): the caller's residual buffer (one 64-row block per half-tile) or a
   // small per-CTA scratch when no backward will follow
   __half* hbuf = hidden ? static_cast<__half*>(hidden) : reinterpret_cast<__half*>(ws + w.h_scratch);
   const uint64_t hrows = static_cast<uint64_t>(hidden ? max_tiles : w.scratch_tiles) * kTileM;
@@ -178,7 +178,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   float* bias2 = reinterpret_cast<float*>(ws + w.bias2);
   float4* coef = reinterpret_cast<float4*>(ws + w.coef);
   __half* g_ring = reinterpret_cast<__half*>(ws + w.g_ring);
-  // activations: the forward's residual buffer (rows = lattice tile * 128) or, recomputed, a ring like g's
+  // activations: the forward's residual buffer (rows = half-tile id * 64) or, recomputed, a ring like g's
   __half* h_src = hidden ? const_cast<__half*>(static_cast<const __half*>(hidden))
                          : reinterpret_cast<__half*>(ws + w.h_ring);
   const uint64_t ring_rows = static_cast<uint64_t>(ring_tiles) * kTileM;
@@ -211,7 +211,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   rc = rb::make_tmap_2d(&tmWmn, Wb, 2, w.Hp, w.Vp, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
   // activations: 64 x 64 boxes (one half-tile), K-major for the logit recompute and MN-major for the dW operand;
-  // gradient ring: 64 x 128 K-major boxes for dh (one lattice tile per CTA of a pair), 64 x 64 boxes for the MN-major dW operand
+  // gradient ring: 64 x 128 K-major boxes for dh (two work-list slots per CTA of a pair), 64 x 64 boxes for the MN-major dW operand
   rc = rb::make_tmap_2d(&tmHk, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
   rc = rb::make_tmap_2d(&tmHk2, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 128);

@@ -8,7 +8,7 @@
 // half-tile) per tcgen05.ld: both reductions are plain register sums, tanh' is recomputed from 8 enc + 4 pred
 // values per thread (MUFU is otherwise idle here), and the fp32 atomics are coalesced over k.
 //   A operand: W^T block (128 k x 64 v) = MN-major view of the fp16 W[Vp,Hp] buffer (TMA, two 64x64 boxes)
-//   B operand: gradient ring g [ring_rows, Vp] fp16, K-major (TMA, one 64 x 256 box = two lattice tiles)
+//   B operand: gradient ring g [ring_rows, Vp] fp16, K-major (TMA, one 64 x 128 box per CTA = two work-list slots)
 // Work item of a CTA PAIR = (four half-tiles of the work list = 256 cells, block of 256 hidden units): one tcgen05.mma.cta_group::2
 // with M = 256; each CTA stages its own 128 hidden units of W^T and HALF of the gradient box (two half-tiles), so
 // the L2 -> shared-memory traffic is 64 instead of 96 bytes per SM and clock.  Accumulators ping-pong between the two
@@ -24,7 +24,7 @@ namespace {
 constexpr int kStages = 6;
 constexpr int kBytesA = kBK * 128 * 2;          // 16 KB: 64 v x 128 k (this CTA's hidden units)
 constexpr int kBytesB = (kBN / 2) * kBK * 2;    // 16 KB: this CTA's 128 of the item's 256 cells x 64 v
-constexpr int kEpiSets = 2;                       // epilogue warp sets; set e handles lattice tile e of the item
+constexpr int kEpiSets = 2;                       // epilogue warp sets; set e handles slots 2e, 2e+1 of the item
 constexpr int kNumThreads = 64 + 128 * kEpiSets;
 constexpr int kTmemCols = 512;
 

@@ -10,7 +10,7 @@
 // finer rounding than bf16 at the same tensor-core rate; accumulation is fp32 in TMEM.)
 //
 // Structure (persistent CTA PAIRS, one CTA per SM; work unit per CTA = 128 GEMM rows = TWO half-tiles of 16(t) x 4(u)
-// lattice cells -- in the forward the two halves of one 16 x 8 tile, in the backward any two entries of the list of
+// lattice cells -- in the forward two consecutive half-tiles, in the backward any two entries of the list of
 // half-tiles that carry non-zero gradients; the two 128-row units of a pair form one M=256 tcgen05.mma.cta_group::2
 // issued by the pair's leader):
 //   * The hidden activations h = tanh(enc+pred) of a tile are produced ONCE, as fp16 rows of a global buffer
@@ -104,7 +104,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const int nk = p.Hp / kBK;
   const int npass = p.Vp / kBN;
 
-  // half-tile id (2 * lattice tile + half) of sub-slot s of unit q, or -1 past the end of the list
+  // half-tile id of sub-slot s of unit q, or -1 past the end of the list
   auto half_id = [&](int q, int s) -> int {
     const int slot = p.slot_begin + 2 * q + s;
     if (q >= nunits || slot >= slot_end) return -1;

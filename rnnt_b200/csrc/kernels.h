@@ -113,7 +113,7 @@ int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, i
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
                 const float* gscale, const int* T_len, const int* U_len, int B, int T, int U1, float4* coef,
                 cudaStream_t stream);
-// flags / sub_list are indexed by half-tile (2 per lattice tile)
+// flags / sub_list are indexed by half-tile id
 int launch_tile_activity(const float4* coef, const int* T_len, const int* U_len, const int* tile_off, int B, int T,
                          int U1, long long max_tiles, int dense, unsigned char* flags, int* sub_list, int* n_active,
                          cudaStream_t stream);

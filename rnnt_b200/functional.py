@@ -20,7 +20,7 @@ _DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(3 << 30)))
 _SAVE_HIDDEN = os.environ.get("RNNT_B200_SAVE_HIDDEN", "1") != "0"
 
 # Optional bookkeeping for bench.py / tests: when enabled, every fused backward leaves a 2-element device tensor
-# (active lattice tiles, total lattice tiles) here.  Off by default (costs two tiny copies per step).
+# (active half-tiles, total half-tiles) here.  Off by default (costs two tiny copies per step).
 COLLECT_BACKWARD_STATS = False
 _last_backward_stats = None
 _last_decode_phase_cycles = None   # int64[8] cycle counters of the last decode kernel (P1..P6, -, grid barriers)
@@ -175,7 +175,7 @@ def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_length
     audio_frame (B,T,H) and text_frame (B,U+1,H) are the (already projected) joint inputs; weight (V,H) / bias (V)
     are joint_ln's parameters.  Per-utterance costs when reduction="none".  validate=True performs torchaudio's
     host-side length checks (one device sync, as the reference does); pass False on the hot loop.
-    skip_zero_tiles=False makes the backward process every lattice tile, including those whose fp16 logit-gradients
+    skip_zero_tiles=False makes the backward process every half-tile (16 t x 4 u lattice block), including those whose fp16 logit-gradients
     are identically zero (same result, more work).  save_hidden: keep the fp16 activations tanh(a+p) from the forward
     for the backward (default; the reference's autograd keeps them in fp32) or recompute them there (False: the saved
     state shrinks to 20 bytes per lattice cell).
