@@ -27,7 +27,11 @@
 extern "C" {
 #endif
 
-#define RNNT_B200_ABI_VERSION 2
+#define RNNT_B200_ABI_VERSION 3
+
+/* `flags` of rnnt_b200_joint_loss_bwd / rnnt_b200_workspace_bytes */
+#define RNNT_B200_ALL_TILES 1      /* process every half-tile, also those whose fp16 logit-gradients are all zero */
+#define RNNT_B200_DETERMINISTIC 2  /* cross-CTA sums in 64-bit fixed point: bit-identical gradients run to run */
 
 int rnnt_b200_abi_version(void);
 const char* rnnt_b200_last_error(void);
@@ -43,37 +47,48 @@ size_t rnnt_b200_hidden_bytes(int B, int T, int U1, int H);
 
 /* Workspace sizes in bytes.  ring_tiles = number of 128-cell tiles the backward's 16-bit gradient (and, without a
  * hidden residual, activation) ring holds at once (fixed size, independent of B*T*U1); the backward walks the batch in
- * chunks of that size.  have_hidden = 1 if `hidden` will be passed to the calls (smaller workspaces). */
-int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
+ * chunks of that size.  have_hidden = 1 if `hidden` will be passed to the calls (smaller workspaces).  flags = the
+ * flags the backward will be called with (RNNT_B200_DETERMINISTIC adds 8 bytes per gradient element). */
+int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden, int flags,
                               size_t* fwd_bytes, size_t* bwd_bytes);
 
 /* Fused joint + loss forward.  Replaces rnnt/joint.py:25-39 followed by rnnt/model.py:35-41 (reduction="none").
- *   enc  (B,T,H) fp32 with element strides (enc_sb, enc_st, 1)      pred (B,U1,H) fp32 contiguous
- *   W    (V,H) fp32 (joint_ln.weight)                                bias (V) fp32 (joint_ln.bias)
+ *   enc  (B,T,H) fp32 with element strides (enc_sb, enc_st, enc_sh): either H-contiguous (enc_sh = 1, enc_sb and
+ *        enc_st multiples of 4) or T-contiguous (enc_st = 1) -- the permuted view of the encoder's (B,H,T) output
+ *        that rnnt/model.py:27-28 hands to the joint; it is read in place, no transposed copy is made
+ *   pred (B,U1,H) fp32 contiguous     W (V,H) fp32 (joint_ln.weight)     bias (V) fp32 (joint_ln.bias)
  * Outputs (all fully written for valid cells): costs (B), lp (B,T,U1,2) = log p(blank), log p(label),
  * lse (B,T,U1), alpha (B,T,U1), beta (B,T,U1).  These five are the residuals the backward consumes.
  * hidden (optional, rnnt_b200_hidden_bytes, 128-byte aligned): receives the fp16 activations for the backward; NULL
  * keeps them in a small per-SM scratch inside the workspace (loss-only evaluation, or a recomputing backward).
- * status (optional, may be NULL): device int set to 1 if any length is out of range. */
-int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
-                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
-                             int B, int T, int U1, int H, int V, int blank, float* costs, float* lp, float* lse,
-                             float* alpha, float* beta, void* hidden, int32_t* status, void* workspace,
-                             size_t workspace_bytes, void* stream);
+ * status (optional, may be NULL): device int set to 1 if any length is out of range (T_b outside [1,T], U_b outside
+ * [0,U1-1]; torchaudio raises for these).  Independently of `status`, every cost is NaN in that case. */
+int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, int64_t enc_sh, const float* pred,
+                             const float* W, const float* bias, const int32_t* targets, const int32_t* T_len,
+                             const int32_t* U_len, int B, int T, int U1, int H, int V, int blank, float* costs,
+                             float* lp, float* lse, float* alpha, float* beta, void* hidden, int32_t* status,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Fused backward.  Replaces RnntLoss.backward + autograd through rnnt/joint.py:32-39.
  * dcost (B) = d loss / d cost_b (1/B for reduction="mean"); clamp <= 0 disables gradient clamping.
  * hidden = the buffer the forward filled, or NULL to recompute the activations (memory-lean mode).
- * Outputs are overwritten: d_enc (B,T,H) contiguous, d_pred (B,U1,H), dW (V,H), dbias (V), all fp32.
+ * Outputs are overwritten, all fp32: d_enc = a dense (B,T,H) tensor (strides (T*H, H, 1)) or a dense (B,H,T) tensor
+ * viewed as (B,T,H) (strides (T*H, 1, T): the gradient lands in the encoder's own layout), d_pred (B,U1,H), dW (V,H),
+ * dbias (V) -- dW / dbias may point into a flat all-reduce bucket.
  * Half-tiles (16 t x 4 u lattice blocks) whose scaled logit-gradients are all below fp16 resolution (occupancy < 2^-25
- * of max|dcost|) are exactly zero in the gradient ring and are skipped; flags bit 0 = 1 disables the skipping (every
- * half-tile that holds a valid cell is processed). */
-int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
-                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
-                             int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
-                             const float* alpha, const float* beta, const void* hidden, const float* dcost,
-                             float clamp, float* d_enc, float* d_pred, float* dW, float* dbias, int64_t ring_tiles,
-                             int flags, void* workspace, size_t workspace_bytes, void* stream);
+ * of max|dcost|) are exactly zero in the gradient ring and are skipped; RNNT_B200_ALL_TILES disables the skipping.
+ * RNNT_B200_DETERMINISTIC replaces the fp32 atomics (d_enc, d_pred, dW, dbias are sums over CTAs) by 64-bit
+ * fixed-point accumulation, which is order-independent: gradients are bit-identical from run to run.
+ * dw_done_event (optional cudaEvent_t, may be NULL) is recorded on `stream` as soon as dW and dbias are final, before
+ * the activation-gradient GEMM of the last chunk is enqueued, so a data-parallel caller can overlap the all-reduce of
+ * the weight gradients (rnnt/train.py:67-68 DDP) with the rest of the backward. */
+int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, int64_t enc_sh, const float* pred,
+                             const float* W, const float* bias, const int32_t* targets, const int32_t* T_len,
+                             const int32_t* U_len, int B, int T, int U1, int H, int V, int blank, const float* lp,
+                             const float* lse, const float* alpha, const float* beta, const void* hidden,
+                             const float* dcost, float clamp, float* d_enc, int64_t denc_sb, int64_t denc_st,
+                             int64_t denc_sh, float* d_pred, float* dW, float* dbias, int64_t ring_tiles, int flags,
+                             void* dw_done_event, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Loss on already materialised logits (B,T,U1,V) fp32 contiguous -- the literal torchaudio.functional.rnnt_loss
  * call of rnnt/model.py:35-41 for callers that hold logits (e.g. eval.py:76 style uses).  fwd writes costs and the
@@ -128,7 +143,7 @@ int rnnt_b200_profile_end(float* ms /*[8]*/, int64_t* launches /*[8]*/);
  *   offsets[1] W as fp16 [Vp, Hp] (zero padded)       offsets[2] bias * log2(e) [Vp] (padding = -1e30)
  *   offsets[3] gradient coefficients (B,T,U1,4) fp32   offsets[4] gradient ring g [ring_tiles*128, Vp] fp16
  *   offsets[5] activation ring h [ring_tiles*128, Hp] fp16 (-1 with have_hidden)
- *   offsets[6] bytes that satisfy both the forward and the backward call
+ *   offsets[6] bytes that satisfy both the forward and the backward call (any flags)
  *   offsets[7] work list of active half-tiles (int32 ids); ring rows [64 i, 64 i + 64) = entry i.
  * Hp / Vp = H / V rounded up to multiples of 64 / 256. */
 int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,

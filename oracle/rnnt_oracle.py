@@ -171,15 +171,18 @@ def logit_grads(logits, targets, T_len, U_len, blank, lse, lpB, lpE, alpha, beta
     return g
 
 
-def loss_and_grads(enc, pred, W, b, targets, T_len, U_len, blank=-1, dcost=None, fast=True):
+def loss_and_grads(enc, pred, W, b, targets, T_len, U_len, blank=-1, dcost=None, fast=True, audio_ln=None,
+                   text_ln=None):
     """Full path rnnt/joint.py:25-39 -> rnnt/model.py:35-41 -> autograd (train.py:134).
 
     Returns dict(costs[B], d_enc, d_pred, dW, db, lse, lpB, lpE, alpha, beta) in fp64.
     dcost defaults to ones (reduction='none' summed); pass 1/B for reduction='mean'.
+    audio_ln / text_ln = (weight, bias) of the optional pre-projections (joint.py:8-12,26-30): enc / pred are then
+    the RAW inputs, d_enc / d_pred their gradients, and dWa, dba, dWt, dbt are added to the result.
     """
     enc = np.asarray(enc, np.float64); pred = np.asarray(pred, np.float64)
     W = np.asarray(W, np.float64); b = np.asarray(b, np.float64)
-    h = joint_hidden(enc, pred)
+    h = joint_hidden(enc, pred, audio_ln, text_ln)
     logits = h @ W.T + b
     lse, lpB, lpE = log_probs(logits, targets, blank)
     alpha, beta, costs = (lattice_fast if fast else lattice)(lpB, lpE, T_len, U_len)
@@ -189,8 +192,21 @@ def loss_and_grads(enc, pred, W, b, targets, T_len, U_len, blank=-1, dcost=None,
     dW = g2.T @ h2                      # autograd of joint_ln, joint.py:39
     db = g2.sum(0)
     dz = (g2 @ W).reshape(h.shape) * (1.0 - h * h)   # tanh backward, joint.py:37
-    return dict(costs=costs, d_enc=dz.sum(2), d_pred=dz.sum(1), dW=dW, db=db,
-                lse=lse, lpB=lpB, lpE=lpE, alpha=alpha, beta=beta)
+    out = dict(costs=costs, d_enc=dz.sum(2), d_pred=dz.sum(1), dW=dW, db=db,
+               lse=lse, lpB=lpB, lpE=lpE, alpha=alpha, beta=beta)
+    if audio_ln is not None:            # autograd of audio_ln, joint.py:26-27
+        Wa = np.asarray(audio_ln[0], np.float64)
+        da = out["d_enc"]
+        out["dWa"] = da.reshape(-1, da.shape[-1]).T @ enc.reshape(-1, enc.shape[-1])
+        out["dba"] = da.reshape(-1, da.shape[-1]).sum(0)
+        out["d_enc"] = da @ Wa
+    if text_ln is not None:             # autograd of text_ln, joint.py:29-30
+        Wt = np.asarray(text_ln[0], np.float64)
+        dt = out["d_pred"]
+        out["dWt"] = dt.reshape(-1, dt.shape[-1]).T @ pred.reshape(-1, pred.shape[-1])
+        out["dbt"] = dt.reshape(-1, dt.shape[-1]).sum(0)
+        out["d_pred"] = dt @ Wt
+    return out
 
 
 # ----------------------------------------------------------------------------- predictor + decode

@@ -7,6 +7,9 @@ import os
 from .build import LIB_PATH
 
 _lib = None
+ABI_VERSION = 3
+FLAG_ALL_TILES = 1        # RNNT_B200_ALL_TILES
+FLAG_DETERMINISTIC = 2    # RNNT_B200_DETERMINISTIC
 
 _i32p = C.c_void_p   # device pointers are passed as integers
 _f32p = C.c_void_p
@@ -17,13 +20,15 @@ _SIGNATURES = {
     "rnnt_b200_last_error": (C.c_char_p, []),
     "rnnt_b200_max_tiles": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "rnnt_b200_hidden_bytes": (C.c_size_t, [C.c_int] * 4),
-    "rnnt_b200_workspace_bytes": (C.c_int, [C.c_int] * 5 + [C.c_int64, C.c_int, C.POINTER(C.c_size_t),
+    "rnnt_b200_workspace_bytes": (C.c_int, [C.c_int] * 5 + [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_size_t),
                                                            C.POINTER(C.c_size_t)]),
-    "rnnt_b200_joint_loss_fwd": (C.c_int, [_f32p, C.c_int64, C.c_int64, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p]
-                                 + [C.c_int] * 6 + [_f32p] * 5 + [_ptr, _i32p, _ptr, C.c_size_t, _ptr]),
-    "rnnt_b200_joint_loss_bwd": (C.c_int, [_f32p, C.c_int64, C.c_int64, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p]
-                                 + [C.c_int] * 6 + [_f32p] * 4 + [_ptr, _f32p, C.c_float] + [_f32p] * 4
-                                 + [C.c_int64, C.c_int, _ptr, C.c_size_t, _ptr]),
+    "rnnt_b200_joint_loss_fwd": (C.c_int, [_f32p, C.c_int64, C.c_int64, C.c_int64, _f32p, _f32p, _f32p, _i32p, _i32p,
+                                           _i32p] + [C.c_int] * 6 + [_f32p] * 5
+                                 + [_ptr, _i32p, _ptr, C.c_size_t, _ptr]),
+    "rnnt_b200_joint_loss_bwd": (C.c_int, [_f32p, C.c_int64, C.c_int64, C.c_int64, _f32p, _f32p, _f32p, _i32p, _i32p,
+                                           _i32p] + [C.c_int] * 6 + [_f32p] * 4 + [_ptr, _f32p, C.c_float]
+                                 + [_f32p, C.c_int64, C.c_int64, C.c_int64] + [_f32p] * 3
+                                 + [C.c_int64, C.c_int, _ptr, _ptr, C.c_size_t, _ptr]),
     "rnnt_b200_loss_dense_fwd": (C.c_int, [_f32p, _i32p, _i32p, _i32p] + [C.c_int] * 5 + [_f32p] * 5 + [_ptr]),
     "rnnt_b200_loss_dense_bwd": (C.c_int, [_f32p, _i32p, _i32p, _i32p] + [C.c_int] * 5 + [_f32p] * 5
                                  + [C.c_float, _f32p, _f32p, _ptr]),
@@ -63,7 +68,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)   # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.rnnt_b200_abi_version() != 2:
+        if handle.rnnt_b200_abi_version() != ABI_VERSION:
             raise RuntimeError("rnnt_b200: ABI version mismatch between Python host code and librnnt_b200.so")
         _lib = handle
     return _lib

@@ -17,13 +17,13 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t tile_off, wb, bias2, h_scratch, coef, flags, tile_list, g_ring, h_ring, total_fwd, total_bwd;
+  size_t tile_off, wb, bias2, h_scratch, coef, flags, tile_list, g_ring, h_ring, fx, total_fwd, total_bwd;
   int Hp, Vp, scratch_tiles;
 };
 
 // have_hidden: the caller supplies the activation residual buffer (rnnt_b200_hidden_bytes).  Then the forward needs
 // no per-CTA activation scratch and the backward ring holds the logit-gradients only.
-WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, bool have_hidden) {
+WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, bool have_hidden, bool deterministic = false) {
   WsLayout w;
   w.Hp = round_up(H, 64);
   w.Vp = round_up(V, 256);
@@ -43,21 +43,39 @@ WsLayout ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, bool 
   const size_t ring_rows = static_cast<size_t>(ring_tiles) * kTileM;
   w.g_ring = off;   off = align_up(off + ring_rows * w.Vp * 2, 1024);
   w.h_ring = off;   off = align_up(off + (have_hidden ? 0 : ring_rows * w.Hp * 2), 1024);
+  // deterministic mode: int64 fixed-point accumulators for d_enc (B,T,H), d_pred (B,U1,H), dW (V,H), db (V)
+  const size_t fx_elems = static_cast<size_t>(B) * T * H + static_cast<size_t>(B) * U1 * H + static_cast<size_t>(V) * H + V;
+  w.fx = off;       off = align_up(off + (deterministic ? fx_elems * 8 : 0), 1024);
   w.total_bwd = off;
   return w;
 }
 
-int check_common(const void* enc, int64_t& enc_sb, int64_t& enc_st, const void* pred, int B, int T, int U1, int H,
-                 int V, int* blank) {
+// Encoder-feature layouts the kernels read directly (element strides of the logical (B,T,H) tensor):
+//   H-contiguous: (sb, st >= H, 1), sb and st multiples of 4 (16-byte vector loads), or
+//   T-contiguous: (sb, 1, sh >= T) -- the permuted view of the encoder's (B,H,T) output, rnnt/model.py:28.
+int check_layout(const char* what, int64_t& sb, int64_t& st, int64_t& sh, int B, int T, int H) {
+  if (sh == 1) {
+    if (T == 1) st = H;                        // strides of size-1 dimensions carry no information
+    if (B == 1) sb = static_cast<int64_t>(T) * st;
+    RB_REQUIRE(st % 4 == 0 && sb % 4 == 0 && st >= H, -3,
+               "%s: H-contiguous layout needs strides (sb, st >= H, 1) that are multiples of 4 elements", what);
+    return 0;
+  }
+  if (T == 1) st = 1;
+  if (B == 1) sb = static_cast<int64_t>(H) * sh;
+  RB_REQUIRE(st == 1 && sh >= T, -3,
+             "%s must be contiguous in the feature dimension (B,T,H) or in the time dimension (view of (B,H,T))", what);
+  return 0;
+}
+
+int check_common(const void* enc, int64_t& enc_sb, int64_t& enc_st, int64_t& enc_sh, const void* pred, int B, int T,
+                 int U1, int H, int V, int* blank) {
   RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && H > 0 && V > 1, -1, "invalid shape B=%d T=%d U1=%d H=%d V=%d", B, T, U1, H, V);
-  if (T == 1) enc_st = H;                      // strides of size-1 dimensions carry no information
-  if (B == 1) enc_sb = static_cast<int64_t>(T) * enc_st;
   RB_REQUIRE(H % 8 == 0, -2, "hidden_features must be a multiple of 8 (got %d)", H);
   RB_REQUIRE(U1 <= 1024, -5, "U+1 must be <= 1024 (got %d)", U1);
   RB_REQUIRE((reinterpret_cast<uintptr_t>(enc) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred) & 15) == 0, -3,
              "enc/pred must be 16-byte aligned");
-  RB_REQUIRE(enc_st % 4 == 0 && enc_sb % 4 == 0 && enc_st >= H, -3,
-             "audio features must be contiguous in the feature dimension with strides that are multiples of 4");
+  if (int rc = check_layout("audio features", enc_sb, enc_st, enc_sh, B, T, H)) return rc;
   if (*blank < 0) *blank += V;
   RB_REQUIRE(*blank >= 0 && *blank < V, -4, "blank index out of range");
   return 0;
@@ -79,10 +97,10 @@ size_t rnnt_b200_hidden_bytes(int B, int T, int U1, int H) {
   return static_cast<size_t>(rnnt_b200_max_tiles(B, T, U1)) * kTileM * round_up(H, 64) * 2;
 }
 
-int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
+int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden, int flags,
                               size_t* fwd_bytes, size_t* bwd_bytes) {
   RB_REQUIRE(B > 0 && T > 0 && U1 > 0 && H > 0 && V > 1 && ring_tiles >= 0, -1, "invalid shape");
-  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, have_hidden != 0);
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, have_hidden != 0, (flags & RNNT_B200_DETERMINISTIC) != 0);
   if (fwd_bytes) *fwd_bytes = w.total_fwd;
   if (bwd_bytes) *bwd_bytes = w.total_bwd;
   return 0;
@@ -90,7 +108,7 @@ int rnnt_b200_workspace_bytes(int B, int T, int U1, int H, int V, int64_t ring_t
 
 int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_tiles, int have_hidden,
                               int64_t* offsets, int* Hp, int* Vp) {
-  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, have_hidden != 0);
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, have_hidden != 0, true);
   offsets[0] = w.tile_off; offsets[1] = w.wb; offsets[2] = w.bias2; offsets[3] = w.coef;
   offsets[4] = w.g_ring; offsets[5] = have_hidden ? -1 : static_cast<int64_t>(w.h_ring);
   offsets[6] = std::max(w.total_fwd, w.total_bwd); offsets[7] = w.tile_list;
@@ -102,16 +120,16 @@ int rnnt_b200_debug_ws_layout(int B, int T, int U1, int H, int V, int64_t ring_t
 int rnnt_b200_lattice(const float* lp, const int32_t* T_len, const int32_t* U_len, int B, int T, int U1, float* alpha,
                       float* beta, float* costs, void* stream) {
   RB_REQUIRE(B > 0 && T > 0 && U1 > 0, -1, "invalid shape");
-  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, static_cast<cudaStream_t>(stream));
+  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, nullptr, static_cast<cudaStream_t>(stream));
 }
 
-int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
-                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
-                             int B, int T, int U1, int H, int V, int blank, float* costs, float* lp, float* lse,
-                             float* alpha, float* beta, void* hidden, int32_t* status, void* workspace,
-                             size_t workspace_bytes, void* stream_) {
+int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, int64_t enc_sh, const float* pred,
+                             const float* W, const float* bias, const int32_t* targets, const int32_t* T_len,
+                             const int32_t* U_len, int B, int T, int U1, int H, int V, int blank, float* costs,
+                             float* lp, float* lse, float* alpha, float* beta, void* hidden, int32_t* status,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
+  int rc = check_common(enc, enc_sb, enc_st, enc_sh, pred, B, T, U1, H, V, &blank);
   if (rc) return rc;
   const WsLayout w = ws_layout(B, T, U1, H, V, 0, hidden != nullptr);
   RB_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 127) == 0, -3, "hidden must be 128-byte aligned");
@@ -142,7 +160,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
 
   rb::JointArgs a{};
-  a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st;
+  a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st; a.enc_sh = enc_sh;
   a.pred = pred; a.pred_sb = static_cast<long long>(U1) * H; a.pred_su = H;
   a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
   a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
@@ -153,21 +171,29 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   a.h_out = hbuf; a.h_map = hidden ? 0 : 2; a.g_ring = nullptr;
   rc = rb::launch_joint_gemm(0, true, tmW, tmH, tmH2, a, 2 * max_tiles, stream);
   if (rc) return rc;
-  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
+  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, tile_off + B + 1, stream);
 }
 
-int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, const float* pred, const float* W,
-                             const float* bias, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,
-                             int B, int T, int U1, int H, int V, int blank, const float* lp, const float* lse,
-                             const float* alpha, const float* beta, const void* hidden, const float* dcost,
-                             float clamp, float* d_enc, float* d_pred, float* dW, float* dbias, int64_t ring_tiles,
-                             int flags, void* workspace, size_t workspace_bytes, void* stream_) {
+int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, int64_t enc_sh, const float* pred,
+                             const float* W, const float* bias, const int32_t* targets, const int32_t* T_len,
+                             const int32_t* U_len, int B, int T, int U1, int H, int V, int blank, const float* lp,
+                             const float* lse, const float* alpha, const float* beta, const void* hidden,
+                             const float* dcost, float clamp, float* d_enc, int64_t denc_sb, int64_t denc_st,
+                             int64_t denc_sh, float* d_pred, float* dW, float* dbias, int64_t ring_tiles, int flags,
+                             void* dw_done_event, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = check_common(enc, enc_sb, enc_st, pred, B, T, U1, H, V, &blank);
+  int rc = check_common(enc, enc_sb, enc_st, enc_sh, pred, B, T, U1, H, V, &blank);
   if (rc) return rc;
+  rc = check_layout("d_enc", denc_sb, denc_st, denc_sh, B, T, H);
+  if (rc) return rc;
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(d_enc) & 15) == 0, -3, "d_enc must be 16-byte aligned");
+  RB_REQUIRE((denc_sh == 1 && denc_st == H && denc_sb == static_cast<int64_t>(T) * H) ||
+                 (denc_st == 1 && denc_sh == T && denc_sb == static_cast<int64_t>(T) * H),
+             -3, "d_enc must be a dense (B,T,H) tensor or a dense (B,H,T) tensor viewed as (B,T,H)");
   RB_REQUIRE(ring_tiles >= 1 && ring_tiles * kTileM < (1ll << 30), -8, "ring_tiles out of range");
   RB_REQUIRE(H % 4 == 0, -2, "hidden_features must be a multiple of 4");
-  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, hidden != nullptr);
+  const bool deterministic = (flags & RNNT_B200_DETERMINISTIC) != 0;
+  const WsLayout w = ws_layout(B, T, U1, H, V, ring_tiles, hidden != nullptr, deterministic);
   RB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total_bwd, -7, "workspace too small: need %zu bytes",
              w.total_bwd);
   RB_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 127) == 0, -3, "hidden must be 128-byte aligned");
@@ -184,10 +210,21 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   const uint64_t ring_rows = static_cast<uint64_t>(ring_tiles) * kTileM;
   const int h_map = hidden ? 0 : 1;
 
-  RB_CUDA_CHECK(cudaMemsetAsync(d_enc, 0, static_cast<size_t>(B) * T * H * 4, stream));
-  RB_CUDA_CHECK(cudaMemsetAsync(d_pred, 0, static_cast<size_t>(B) * U1 * H * 4, stream));
-  RB_CUDA_CHECK(cudaMemsetAsync(dW, 0, static_cast<size_t>(V) * H * 4, stream));
-  RB_CUDA_CHECK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream));
+  // accumulation targets: the fp32 outputs themselves (atomics), or 64-bit fixed-point shadows (deterministic mode)
+  const size_t n_enc = static_cast<size_t>(B) * T * H, n_pred = static_cast<size_t>(B) * U1 * H;
+  const size_t n_w = static_cast<size_t>(V) * H;
+  long long* fx_enc = deterministic ? reinterpret_cast<long long*>(ws + w.fx) : nullptr;
+  long long* fx_pred = deterministic ? fx_enc + n_enc : nullptr;
+  long long* fx_w = deterministic ? fx_pred + n_pred : nullptr;
+  long long* fx_b = deterministic ? fx_w + n_w : nullptr;
+  if (deterministic) {
+    RB_CUDA_CHECK(cudaMemsetAsync(fx_enc, 0, (n_enc + n_pred + n_w + V) * 8, stream));
+  } else {
+    RB_CUDA_CHECK(cudaMemsetAsync(d_enc, 0, n_enc * 4, stream));
+    RB_CUDA_CHECK(cudaMemsetAsync(d_pred, 0, n_pred * 4, stream));
+    RB_CUDA_CHECK(cudaMemsetAsync(dW, 0, n_w * 4, stream));
+    RB_CUDA_CHECK(cudaMemsetAsync(dbias, 0, static_cast<size_t>(V) * 4, stream));
+  }
 
   const int64_t max_tiles = rnnt_b200_max_tiles(B, T, U1);
   float* gscale = reinterpret_cast<float*>(tile_off + B + 2);
@@ -199,7 +236,8 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   if (rc) return rc;
   int* n_active = tile_off + B + 4;
   int* sub_list = reinterpret_cast<int*>(ws + w.tile_list);    // active half-tiles, order preserved
-  rc = rb::launch_tile_activity(coef, T_len, U_len, tile_off, B, T, U1, max_tiles, (flags & 1) ? 1 : 0,
+  rc = rb::launch_tile_activity(coef, T_len, U_len, tile_off, B, T, U1, max_tiles,
+                                (flags & RNNT_B200_ALL_TILES) ? 1 : 0,
                                 reinterpret_cast<unsigned char*>(ws + w.flags), sub_list, n_active, stream);
   if (rc) return rc;
 
@@ -223,14 +261,16 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
   rc = rb::make_tmap_2d(&tmHmn, h_src, 2, w.Hp, h_rows, static_cast<uint64_t>(w.Hp) * 2, 64, 64);
   if (rc) return rc;
 
-  // the work list is walked in chunks of as many slots (half-tiles of 64 rows) as the ring holds
+  // The work list is walked in chunks of as many slots (half-tiles of 64 rows) as the ring holds.  Per chunk: G (logit
+  // recompute -> gradient ring), then dW/db, then dh -- the weight gradients come first so that, after the last chunk,
+  // `dw_done_event` lets the caller start their all-reduce while the dh GEMM of that chunk is still running.
   const int64_t max_slots = 2 * max_tiles, ring_slots = 2 * ring_tiles;
   const int64_t nchunks = (max_slots + ring_slots - 1) / ring_slots;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int slot_begin = static_cast<int>(c * ring_slots);
     const int64_t chunk_slots = std::min<int64_t>(ring_slots, max_slots - c * ring_slots);
     rb::JointArgs a{};
-    a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st;
+    a.enc = enc; a.enc_sb = enc_sb; a.enc_st = enc_st; a.enc_sh = enc_sh;
     a.pred = pred; a.pred_sb = static_cast<long long>(U1) * H; a.pred_su = H;
     a.bias2 = bias2; a.targets = targets; a.tgt_ld = U1 - 1;
     a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
@@ -242,20 +282,37 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, c
     rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, tmHk2, a, chunk_slots, stream);
     if (rc) return rc;
 
+    rb::DwArgs g{};
+    g.n_active = n_active; g.sub_list = sub_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
+    g.slot_begin = slot_begin; g.slot_cap = static_cast<int>(ring_slots); g.dW = dW; g.db = dbias; g.gscale = gscale;
+    g.dW_fx = fx_w; g.db_fx = fx_b;
+    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_slots, stream);
+    if (rc) return rc;
+    if (c == nchunks - 1) {
+      if (deterministic) {
+        rc = rb::launch_finalize_fixed(fx_w, dW, 1, V, H, 0, H, 1, gscale, stream);
+        if (rc) return rc;
+        rc = rb::launch_finalize_fixed(fx_b, dbias, 1, 1, V, 0, 0, 1, gscale, stream);
+        if (rc) return rc;
+      }
+      if (dw_done_event) RB_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(dw_done_event), stream));
+    }
+
     rb::DhArgs d{};
-    d.enc = enc; d.enc_sb = enc_sb; d.enc_st = enc_st;
+    d.enc = enc; d.enc_sb = enc_sb; d.enc_st = enc_st; d.enc_sh = enc_sh;
     d.pred = pred; d.pred_sb = static_cast<long long>(U1) * H; d.pred_su = H; d.gscale = gscale; d.sub_list = sub_list; d.n_active = n_active;
     d.T_len = T_len; d.U_len = U_len; d.tile_off = tile_off;
     d.B = B; d.T = T; d.U1 = U1; d.H = H; d.Hp = w.Hp; d.Vp = w.Vp;
     d.slot_begin = slot_begin; d.slot_cap = static_cast<int>(ring_slots);
-    d.d_enc = d_enc; d.d_pred = d_pred;
+    d.d_enc = d_enc; d.denc_sb = denc_sb; d.denc_st = denc_st; d.denc_sh = denc_sh; d.d_pred = d_pred;
+    d.d_enc_fx = fx_enc; d.d_pred_fx = fx_pred;
     rc = rb::launch_dh_gemm(tmG128, tmWmn, d, chunk_slots, stream);
     if (rc) return rc;
-
-    rb::DwArgs g{};
-    g.n_active = n_active; g.sub_list = sub_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
-    g.slot_begin = slot_begin; g.slot_cap = static_cast<int>(ring_slots); g.dW = dW; g.db = dbias; g.gscale = gscale;
-    rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_slots, stream);
+  }
+  if (deterministic) {
+    rc = rb::launch_finalize_fixed(fx_enc, d_enc, B, T, H, denc_sb, denc_st, denc_sh, gscale, stream);
+    if (rc) return rc;
+    rc = rb::launch_finalize_fixed(fx_pred, d_pred, 1, static_cast<long long>(B) * U1, H, 0, H, 1, gscale, stream);
     if (rc) return rc;
   }
   return 0;
@@ -271,7 +328,7 @@ int rnnt_b200_loss_dense_fwd(const float* logits, const int32_t* targets, const 
   RB_REQUIRE(blank >= 0 && blank < V, -4, "blank index out of range");
   int rc = rb::launch_dense_logprobs(logits, targets, U1 - 1, T_len, U_len, B, T, U1, V, blank, lp, lse, stream);
   if (rc) return rc;
-  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, stream);
+  return rb::launch_lattice(lp, T_len, U_len, B, T, U1, alpha, beta, costs, nullptr, stream);
 }
 
 int rnnt_b200_loss_dense_bwd(const float* logits, const int32_t* targets, const int32_t* T_len, const int32_t* U_len,

@@ -85,7 +85,7 @@ __global__ void decode_argmax_kernel(const float* __restrict__ logits, int N, in
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    tokens[r] = si[0];
+    tokens[r] = static_cast<unsigned>(si[0]) < static_cast<unsigned>(V) ? si[0] : 0;   // all-NaN / -inf row -> 0
     if (top2) top2[r] = sb[0] - ss[0];
   }
 }

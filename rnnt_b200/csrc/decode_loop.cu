@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
         }
         __syncthreads();
       }
-      const int tok = s_idx[0];
+      // torch.argmax always returns an in-range index; a row without any finite maximum (all NaN / -inf) maps to 0
+      const int tok = static_cast<unsigned>(s_idx[0]) < static_cast<unsigned>(V) ? s_idx[0] : 0;
       const bool advance = (tok == p.blank) || (p.per[b] >= p.max_per_frame);
       __syncthreads();
       if (tid == 0) {
@@ -388,10 +389,19 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
 
 }  // namespace
 
+// Scratch layout: [8 x int64 phase timers | float regions, each padded to a multiple of 4 floats so that every region
+// starts 16-byte aligned whatever B, V, E are (cp.async / float4 need it) | int regions].
+namespace {
+inline size_t pad4(size_t n) { return (n + 3) & ~static_cast<size_t>(3); }
+constexpr size_t kTimerBytes = 64;
+}  // namespace
+
 size_t greedy_decode_scratch_bytes(int B, int H, int V, int E) {
-  const size_t floats = static_cast<size_t>(B) * (H /*feats*/ + H /*hbuf*/ + V /*logits*/ + 2 * E + 4 * E + E + E + E + H /*lin*/);
-  const size_t ints = static_cast<size_t>(B) * 6 + 16;
-  return floats * 4 + ints * 4 + 256 + 64;   // + 8 x int64 phase timers at the very end
+  const size_t b = static_cast<size_t>(B);
+  const size_t floats = 3 * pad4(b * H) /*feats, hbuf, lin*/ + pad4(b * V) /*logits*/ + pad4(b * 2 * E) + pad4(b * 4 * E) +
+                        3 * pad4(b * E) /*xnew, ynew, z*/;
+  const size_t ints = b * 5 + 16;
+  return kTimerBytes + floats * 4 + ints * 4 + 256;
 }
 
 int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream) {
@@ -406,24 +416,26 @@ int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream) {
   RB_REQUIRE(smem <= 200 * 1024 && klen_max <= 4 * kMaxIt * kThreads, -6,
              "decode kernel supports hidden_features <= 3072 and embedding dim <= 614");
   // carve the scratch
-  float* f = scratch;
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, -3, "decode scratch must be 16-byte aligned");
+  a.prof = reinterpret_cast<long long*>(scratch);          // 8 x int64 at the (aligned) start
+  float* f = scratch + kTimerBytes / sizeof(float);
   const int B = a.B, H = a.H, V = a.V, E = a.E;
-  a.feats = f; f += static_cast<size_t>(B) * H;
-  a.hbuf = f; f += static_cast<size_t>(B) * H;
-  a.logits = f; f += static_cast<size_t>(B) * V;
-  a.xs = f; f += static_cast<size_t>(B) * 2 * E;
-  a.ys = f; f += static_cast<size_t>(B) * 4 * E;
-  a.xnew = f; f += static_cast<size_t>(B) * E;
-  a.ynew = f; f += static_cast<size_t>(B) * E;
-  a.z = f; f += static_cast<size_t>(B) * E;
-  a.lin = f; f += static_cast<size_t>(B) * H;
+  const size_t b = static_cast<size_t>(B);
+  a.feats = f; f += pad4(b * H);
+  a.hbuf = f; f += pad4(b * H);
+  a.logits = f; f += pad4(b * V);
+  a.xs = f; f += pad4(b * 2 * E);
+  a.ys = f; f += pad4(b * 4 * E);
+  a.xnew = f; f += pad4(b * E);
+  a.ynew = f; f += pad4(b * E);
+  a.z = f; f += pad4(b * E);
+  a.lin = f; f += pad4(b * H);
   int* ip = reinterpret_cast<int*>(f);
   a.t_idx = ip; ip += B;
   a.per = ip; ip += B;
   a.emit = ip; ip += B;
   a.rows = ip; ip += 2 * B;
   a.flags = ip; ip += 16;
-  a.prof = reinterpret_cast<long long*>(reinterpret_cast<char*>(scratch) + greedy_decode_scratch_bytes(B, H, V, E) - 64);
   RB_CUDA_CHECK(cudaFuncSetAttribute(greedy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_decode_kernel, kThreads, smem));

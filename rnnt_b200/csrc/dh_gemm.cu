@@ -123,6 +123,9 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
     const int eset = (warp - 2) >> 2;
     const int krow = lane_grp * 32 + lane;      // hidden unit within the block = TMEM lane
     const float inv_s = __ldg(p.gscale + 1);
+    // vector paths for the T-contiguous layouts (api.cu guarantees 16-byte aligned bases)
+    const bool enc_vec = p.enc_st == 1 && p.enc_sh != 1 && ((p.enc_sh | p.enc_sb) & 3) == 0;
+    const bool denc_vec = p.denc_st == 1 && p.denc_sh != 1 && ((p.denc_sh | p.denc_sb) & 3) == 0;
     uint32_t ic = 0;
     for (int item = pair; item < nitems; item += npairs, ++ic) {
       const int cb = item / nhb, hb = item % nhb;
@@ -136,43 +139,68 @@ dh_gemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ 
       for (int hs = eset * (4 / kEpiSets); hs < (eset + 1) * (4 / kEpiSets); ++hs) {   // this set's half-tiles of the item
         const int slot = p.slot_begin + cb * 4 + hs;
         if (slot >= slot_end) break;            // uniform
-        const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, __ldg(p.sub_list + slot));
+        const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, p.T, p.U1, __ldg(p.sub_list + slot));
         float pv[4], su[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           pv[j] = __ldg(p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + j, p.U1 - 1)) * p.pred_su + kk);
           su[j] = 0.f;
         }
-        const float* e_base = p.enc + tc.b * p.enc_sb + kk;
+        const float* e_base = p.enc + tc.b * p.enc_sb + static_cast<long long>(kk) * p.enc_sh;
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {           // 32 columns = t-rows 8q .. 8q+7 x 4 u
           float v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + acc * kBN + hs * 64 + q * 32, v);
+          const int tb = tc.t0 + q * 8;         // first of this thread's 8 frames
           float ev[8];
+          if (enc_vec && tb + 7 < p.T) {        // T-contiguous encoder view: the 8 frames are 32 contiguous bytes
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(e_base + tb));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(e_base + tb) + 1);
+            ev[0] = a0.x; ev[1] = a0.y; ev[2] = a0.z; ev[3] = a0.w; ev[4] = a1.x; ev[5] = a1.y; ev[6] = a1.z; ev[7] = a1.w;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            ev[i] = __ldg(e_base + static_cast<long long>(min(tc.t0 + q * 8 + i, p.T - 1)) * p.enc_st);
+            for (int i = 0; i < 8; ++i) ev[i] = __ldg(e_base + static_cast<long long>(min(tb + i, p.T - 1)) * p.enc_st);
+          }
           tmem_ld_wait();
+          float st[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float st = 0.f;
+            st[i] = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float h = tanh_approx(ev[i] + pv[j]);
               const float dz = v[i * 4 + j] * fmaf(-h, h, 1.f);
-              st += dz;
+              st[i] += dz;
               su[j] += dz;
             }
-            const int t = tc.t0 + q * 8 + i;
-            if (k_ok && t < tc.Tb)
-              atomicAdd(p.d_enc + (static_cast<long long>(tc.b) * p.T + t) * p.H + k, st * inv_s);
+          }
+          if (k_ok) {
+            if (p.d_enc_fx) {
+              long long* dst = p.d_enc_fx + (static_cast<long long>(tc.b) * p.T + tb) * p.H + k;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (tb + i < tc.Tb) fx_add(dst + static_cast<long long>(i) * p.H, st[i]);
+            } else {
+              float* dst = p.d_enc + tc.b * p.denc_sb + static_cast<long long>(k) * p.denc_sh;
+              if (denc_vec && tb + 7 < tc.Tb) {   // gradient in the encoder's own (B,H,T) layout: two 16-byte reductions
+                red_add_v4(dst + tb, st[0] * inv_s, st[1] * inv_s, st[2] * inv_s, st[3] * inv_s);
+                red_add_v4(dst + tb + 4, st[4] * inv_s, st[5] * inv_s, st[6] * inv_s, st[7] * inv_s);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (tb + i < tc.Tb) atomicAdd(dst + static_cast<long long>(tb + i) * p.denc_st, st[i] * inv_s);
+              }
+            }
           }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int u = tc.u0 + j;
-          if (k_ok && u <= tc.Ub)
-            atomicAdd(p.d_pred + (static_cast<long long>(tc.b) * p.U1 + u) * p.H + k, su[j] * inv_s);
+          if (k_ok && u <= tc.Ub) {
+            const long long o = (static_cast<long long>(tc.b) * p.U1 + u) * p.H + k;
+            if (p.d_pred_fx) fx_add(p.d_pred_fx + o, su[j]);
+            else atomicAdd(p.d_pred + o, su[j] * inv_s);
+          }
         }
       }
       tc_fence_before();

@@ -174,7 +174,10 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(a_empty + 8 * sa);
       }
-      if (v < p.V) atomicAdd(p.db + v, dsum * inv_s);
+      if (v < p.V) {
+        if (p.db_fx) fx_add(p.db_fx + v, dsum);
+        else atomicAdd(p.db + v, dsum * inv_s);
+      }
     }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -184,15 +187,18 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
       float acc[32];
       tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + c32 * 32, acc);
       tmem_ld_wait();
-      if (v < p.V) {
+      if (v < p.V && p.dW_fx) {          // deterministic mode: order-independent fixed-point accumulation
+        long long* dst = p.dW_fx + static_cast<long long>(v) * p.H + col0;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (col0 + e < p.H) fx_add(dst + e, acc[e]);
+      } else if (v < p.V) {
         float* dst = p.dW + static_cast<long long>(v) * p.H + col0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (col0 + 4 * q + 3 < p.H) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q),
-                         "f"(acc[4 * q] * inv_s), "f"(acc[4 * q + 1] * inv_s), "f"(acc[4 * q + 2] * inv_s),
-                         "f"(acc[4 * q + 3] * inv_s)
-                         : "memory");
+            red_add_v4(dst + 4 * q, acc[4 * q] * inv_s, acc[4 * q + 1] * inv_s, acc[4 * q + 2] * inv_s,
+                       acc[4 * q + 3] * inv_s);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)

@@ -27,7 +27,7 @@ const char* get_error();
     }                                \
   } while (0)
 
-// 2D row-major tensor [outer][inner] of 2-byte (bf16) or 4-byte (f32) elements, 128-byte swizzle,
+// 2D row-major tensor [outer][inner] of 2-byte (fp16) or 4-byte (f32) elements, 128-byte swizzle,
 // box = box_inner x box_outer elements.  OOB box parts are zero-filled on load and dropped on store.
 int make_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);

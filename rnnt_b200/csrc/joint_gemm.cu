@@ -234,7 +234,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       const int q = base_ + rank;
       const bool mine = q < nunits;
       const int hid = half_id(q, sub);
-      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, max(hid, 0));
+      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, p.T, p.U1, max(hid, 0));
       const int t = tc.t0 + ti, u = tc.u0 + ui;
       const bool valid = hid >= 0 && (t < tc.Tb) && (u <= tc.Ub);
       const long long cell = (static_cast<long long>(tc.b) * p.T + min(t, p.T - 1)) * p.U1 + min(u, p.U1 - 1);
@@ -359,23 +359,56 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (lane == 0) mbar_arrive(h_ready + 8 * (cnt & 1));
         continue;
       }
-      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, hid);
+      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, p.T, p.U1, hid);
       const int row0 = h_row0(q, sub, hid, cnt);
+      // Encoder features arrive either H-contiguous (enc_sh == 1) or, as rnnt/model.py:28 hands them over, as the
+      // (B,T,H) view of the encoder's (B,H,T) output (enc_st == 1, T-contiguous): then the lane's two frames are the
+      // two halves of one 8-byte load per hidden unit, straight from the encoder's buffer (no transpose copy).
+      const bool t_major = p.enc_sh != 1;
+      const int te0 = tc.t0 + tq;                                   // first of this lane's two frames
+      const bool pair_ok = t_major && (te0 + 1 < p.T) && ((p.enc_sh | p.enc_sb) & 1) == 0;
       const float* e_ptr[2];
       const float* p_ptr[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + tq + i, p.T - 1)) * p.enc_st + 8 * c;
+        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(te0 + i, p.T - 1)) * p.enc_st +
+                   static_cast<long long>(8 * c) * p.enc_sh;
         p_ptr[i] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + uq + i, p.U1 - 1)) * p.pred_su + 8 * c;
       }
       float4 e_cur[2][2], p_cur[2][2];
       auto load_chunk = [&](int kc, float4 (&e)[2][2], float4 (&pp)[2][2]) {
         const int col = kc * kBK + 8 * c;
         if (col < p.H) {
+          if (!t_major) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              e[i][0] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK));
+              e[i][1] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK) + 1);
+            }
+          } else {
+            float ev[2][8];
+            const long long koff = static_cast<long long>(kc) * kBK * p.enc_sh;
+            if (pair_ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(e_ptr[0] + koff + j * p.enc_sh));
+                ev[0][j] = v.x; ev[1][j] = v.y;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                ev[0][j] = __ldg(e_ptr[0] + koff + j * p.enc_sh);
+                ev[1][j] = __ldg(e_ptr[1] + koff + j * p.enc_sh);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              e[i][0] = make_float4(ev[i][0], ev[i][1], ev[i][2], ev[i][3]);
+              e[i][1] = make_float4(ev[i][4], ev[i][5], ev[i][6], ev[i][7]);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            e[i][0] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK));
-            e[i][1] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK) + 1);
             pp[i][0] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK));
             pp[i][1] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK) + 1);
           }

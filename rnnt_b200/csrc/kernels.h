@@ -12,8 +12,8 @@
 namespace rb {
 
 struct JointArgs {
-  const float* enc;       // (B,T,H) fp32, H contiguous
-  long long enc_sb, enc_st;
+  const float* enc;       // (B,T,H) fp32 with element strides (enc_sb, enc_st, enc_sh): H-contiguous (enc_sh == 1) or
+  long long enc_sb, enc_st, enc_sh;   // the T-contiguous view of the encoder's (B,H,T) output (enc_st == 1)
   const float* pred;      // (B,U1,H) fp32, H contiguous
   long long pred_sb, pred_su;
   const float* bias2;     // [Vp] bias * log2(e); padding columns hold -1e30
@@ -40,8 +40,8 @@ struct JointArgs {
 };
 
 struct DhArgs {
-  const float* enc;       // (B,T,H) fp32, H contiguous (tanh' is recomputed from the inputs)
-  long long enc_sb, enc_st;
+  const float* enc;       // (B,T,H) fp32, strides as in JointArgs (tanh' is recomputed from the inputs)
+  long long enc_sb, enc_st, enc_sh;
   const float* pred;      // (B,U1,H)
   long long pred_sb, pred_su;
   const float* gscale;    // {S, 1/S}
@@ -52,8 +52,13 @@ struct DhArgs {
   const int* tile_off;
   int B, T, U1, H, Hp, Vp;
   int slot_begin, slot_cap;
-  float* d_enc;          // (B,T,H) fp32, accumulated with atomics (caller zero-fills)
-  float* d_pred;         // (B,U1,H)
+  float* d_enc;          // (B,T,H) fp32 with element strides (denc_sb, denc_st, denc_sh), accumulated with atomics
+  long long denc_sb, denc_st, denc_sh;   // (caller zero-fills)
+  float* d_pred;         // (B,U1,H) contiguous
+  // deterministic mode: order-independent 64-bit fixed-point accumulators (2^-36 units) instead of fp32 atomics;
+  // dense (B,T,H) / (B,U1,H) row-major, converted to d_enc / d_pred by finalize_fixed_kernel
+  long long* d_enc_fx;
+  long long* d_pred_fx;
 };
 
 struct DwArgs {
@@ -66,6 +71,8 @@ struct DwArgs {
   float* dW;             // (V,H) fp32, accumulated with atomics (caller zero-fills)
   float* db;             // (V) fp32, accumulated with atomics (column sums of g, taken from the A stages)
   const float* gscale;   // {S, 1/S}
+  long long* dW_fx;      // deterministic mode: 64-bit fixed-point accumulators (V,H) / (V), else nullptr
+  long long* db_fx;
   int ksplit;
 };
 
@@ -108,8 +115,12 @@ int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, 
                       const float* dcost, float* gscale, cudaStream_t stream);
 int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __half* Wh,
                            float* bias2, cudaStream_t stream);
+// status (optional): device flag written by the tile table; a non-zero flag turns every cost into NaN
 int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, int T, int U1, float* alpha,
-                   float* beta, float* costs, cudaStream_t stream);
+                   float* beta, float* costs, const int* status, cudaStream_t stream);
+// deterministic mode: out[i] = fx[i] * 2^-36 * gscale[1]; dst strides in elements (n0 x n1 x n2 logical shape)
+int launch_finalize_fixed(const long long* fx, float* out, long long n0, long long n1, long long n2, long long s0,
+                          long long s1, long long s2, const float* gscale, cudaStream_t stream);
 int launch_coef(const float* lp, const float* lse, const float* alpha, const float* beta, const float* dcost,
                 const float* gscale, const int* T_len, const int* U_len, int B, int T, int U1, float4* coef,
                 cudaStream_t stream);

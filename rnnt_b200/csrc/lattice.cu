@@ -47,6 +47,7 @@ __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __re
     acc += ((Tb + kTileT - 1) / kTileT) * ((Ub + 1 + kHalfU - 1) / kHalfU);     // half-tiles of 16(t) x 4(u)
     tile_off[b + 1] = acc;
   }
+  tile_off[B + 1] = bad;          // internal status word: the lattice kernel turns the costs into NaN when it is set
   if (err_flag) *err_flag = bad;
 }
 
@@ -79,7 +80,7 @@ constexpr int kPre = 8;
 template <bool BETA>
 __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, float* __restrict__ out,
                                              float* __restrict__ costs_b, int Tb, int Ub, int U1, int u, float* sh0,
-                                             float* sh1) {
+                                             float* sh1, bool poison) {
   // The step time of this kernel is (instructions per step) x (dependent-issue latency): one warp per scheduler, no
   // other work to hide behind.  So everything that is not the recursion itself is hoisted out of the step: the
   // activity test is one unsigned compare, the store walks a pointer, the emit log-prob of the last column is -inf
@@ -143,12 +144,14 @@ __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, flo
 #pragma unroll
     for (int i = 0; i < kPre; ++i) cur[i] = nxt[i];
   }
-  if (BETA && u == 0) *costs_b = -last;                  // beta(0,0) is the last cell column 0 visits
+  // beta(0,0) is the last cell column 0 visits.  An out-of-range length anywhere in the batch (status word of the tile
+  // table; torchaudio raises for these) turns every cost into NaN, so the error cannot pass silently without a sync.
+  if (BETA && u == 0) *costs_b = poison ? __int_as_float(0x7fc00000) : -last;
 }
 
 __global__ void lattice_kernel(const float* __restrict__ lp, const int* __restrict__ T_len,
                                const int* __restrict__ U_len, int T, int U1, float* __restrict__ alpha,
-                               float* __restrict__ beta, float* __restrict__ costs) {
+                               float* __restrict__ beta, float* __restrict__ costs, const int* __restrict__ status) {
   extern __shared__ float sh[];   // 2 x (blockDim.x + 2)
   const int b = blockIdx.x;
   const int u = threadIdx.x;
@@ -165,8 +168,9 @@ __global__ void lattice_kernel(const float* __restrict__ lp, const int* __restri
   __syncthreads();
   const long long off = static_cast<long long>(b) * T * U1;
   const float2* lp2 = reinterpret_cast<const float2*>(lp) + off;
-  if (blockIdx.y == 1) lattice_walk<true>(lp2, beta + off, costs + b, Tb, Ub, U1, u, sh0, sh1);
-  else lattice_walk<false>(lp2, alpha + off, costs + b, Tb, Ub, U1, u, sh0, sh1);
+  const bool poison = status != nullptr && *status != 0;
+  if (blockIdx.y == 1) lattice_walk<true>(lp2, beta + off, costs + b, Tb, Ub, U1, u, sh0, sh1, poison);
+  else lattice_walk<false>(lp2, alpha + off, costs + b, Tb, Ub, U1, u, sh0, sh1, poison);
 }
 
 __global__ void coef_kernel(const float* __restrict__ lp, const float* __restrict__ lse,
@@ -210,7 +214,7 @@ __global__ void tile_activity_kernel(const float4* __restrict__ coef, const int*
   const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
   for (int hid = w0; hid < total; hid += nw) {
-    const TileCoord tc = decode_half(tile_off, T_len, U_len, B, hid);
+    const TileCoord tc = decode_half(tile_off, T_len, U_len, B, T, U1, hid);
     float mx = 0.f;
     int any_valid = 0;
 #pragma unroll
@@ -321,7 +325,30 @@ __global__ void dense_grads_kernel(const float* __restrict__ logits, const int* 
   }
 }
 
+// deterministic mode: 64-bit fixed-point accumulators -> fp32 outputs (possibly strided, e.g. the encoder's (B,H,T) layout)
+__global__ void finalize_fixed_kernel(const long long* __restrict__ fx, float* __restrict__ out, long long n0,
+                                      long long n1, long long n2, long long s0, long long s1, long long s2,
+                                      const float* __restrict__ gscale) {
+  const long long n = n0 * n1 * n2;
+  const double mul = kFxInv * static_cast<double>(gscale[1]);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i2 = i % n2, i1 = (i / n2) % n1, i0 = i / (n2 * n1);
+    out[i0 * s0 + i1 * s1 + i2 * s2] = static_cast<float>(static_cast<double>(fx[i]) * mul);
+  }
+}
+
 }  // namespace
+
+int launch_finalize_fixed(const long long* fx, float* out, long long n0, long long n1, long long n2, long long s0,
+                          long long s1, long long s2, const float* gscale, cudaStream_t stream) {
+  ProfScope prof_(kProfPrep, stream);
+  const long long n = n0 * n1 * n2;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  finalize_fixed_kernel<<<grid, 256, 0, stream>>>(fx, out, n0, n1, n2, s0, s1, s2, gscale);
+  RB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, int* tile_off, int* err_flag,
                       const float* dcost, float* gscale, cudaStream_t stream) {
@@ -342,12 +369,12 @@ int launch_convert_weights(const float* W, const float* bias, int V, int H, int 
 }
 
 int launch_lattice(const float* lp, const int* T_len, const int* U_len, int B, int T, int U1, float* alpha,
-                   float* beta, float* costs, cudaStream_t stream) {
+                   float* beta, float* costs, const int* status, cudaStream_t stream) {
   ProfScope prof_(kProfLattice, stream);
   const int threads = ((U1 + 31) / 32) * 32;
   RB_REQUIRE(threads <= 1024, -5, "lattice kernel supports U+1 <= 1024 (got %d)", U1);
   const size_t smem = 2 * (threads + 2) * sizeof(float);
-  lattice_kernel<<<dim3(B, 2), threads, smem, stream>>>(lp, T_len, U_len, T, U1, alpha, beta, costs);
+  lattice_kernel<<<dim3(B, 2), threads, smem, stream>>>(lp, T_len, U_len, T, U1, alpha, beta, costs, status);
   RB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -18,12 +18,24 @@ _DEFAULT_RING_BYTES = int(os.environ.get("RNNT_B200_RING_BYTES", str(3 << 30)))
 # Keep h = tanh(enc + pred) (fp16, 2*H bytes per lattice cell) from the forward for the backward (default), or
 # recompute it there (RNNT_B200_SAVE_HIDDEN=0: residuals shrink to 20 bytes per cell, the backward runs ~10 % slower).
 _SAVE_HIDDEN = os.environ.get("RNNT_B200_SAVE_HIDDEN", "1") != "0"
+# Bit-identical gradients from run to run (64-bit fixed-point accumulation instead of fp32 atomics); also switched on
+# by torch.use_deterministic_algorithms(True) or per call (deterministic=True).
+_DETERMINISTIC = os.environ.get("RNNT_B200_DETERMINISTIC", "0") != "0"
 
 # Optional bookkeeping for bench.py / tests: when enabled, every fused backward leaves a 2-element device tensor
 # (active half-tiles, total half-tiles) here.  Off by default (costs two tiny copies per step).
 COLLECT_BACKWARD_STATS = False
 _last_backward_stats = None
 _last_decode_phase_cycles = None   # int64[8] cycle counters of the last decode kernel (P1..P6, -, grid barriers)
+
+# Data-parallel hook (rnnt_b200.parallel.WeightGradBucket): when set, the fused backward writes dW / db straight into the
+# sink's flat bucket and tells it the moment they are final, so the all-reduce overlaps the activation-gradient GEMM.
+_weight_grad_sink = None
+
+
+def set_weight_grad_sink(sink) -> None:
+    global _weight_grad_sink
+    _weight_grad_sink = sink
 
 
 def last_backward_stats():
@@ -76,11 +88,32 @@ def pick_ring_tiles(B: int, T: int, U1: int, H: int, V: int, ring_bytes: Optiona
     return (max_tiles + nchunks - 1) // nchunks
 
 
-def workspace_bytes(B, T, U1, H, V, ring_tiles, have_hidden=False):
+def workspace_bytes(B, T, U1, H, V, ring_tiles, have_hidden=False, flags=0):
     fwd, bwd = C.c_size_t(0), C.c_size_t(0)
-    _lib.check(_lib.lib().rnnt_b200_workspace_bytes(B, T, U1, H, V, ring_tiles, int(bool(have_hidden)),
+    _lib.check(_lib.lib().rnnt_b200_workspace_bytes(B, T, U1, H, V, ring_tiles, int(bool(have_hidden)), int(flags),
                                                     C.byref(fwd), C.byref(bwd)), "workspace_bytes")
     return fwd.value, bwd.value
+
+
+def _kernel_layout(x):
+    """`x` itself if the kernels can read its (B,T,H) layout in place -- H-contiguous, or the T-contiguous permuted view
+    of a dense (B,H,T) tensor (what rnnt/model.py:27-28 passes to the joint) -- else a contiguous copy."""
+    B, T, H = x.shape
+    if x.data_ptr() % 16 == 0:
+        if x.stride(2) == 1 and x.stride(1) % 4 == 0 and x.stride(0) % 4 == 0 and x.stride(1) >= H:
+            return x
+        if x.stride(1) == 1 and x.stride(2) >= T:
+            return x
+    return x.contiguous()
+
+
+def _grad_like(x):
+    """Gradient buffer for the (B,T,H) input `x`: same memory layout when that layout is dense (a dense (B,H,T) tensor
+    viewed as (B,T,H) gets its gradient in (B,H,T) order, so the encoder's backward sees a contiguous tensor)."""
+    B, T, H = x.shape
+    if x.stride(1) == 1 and x.stride(2) == T and (B == 1 or x.stride(0) == H * T) and T > 1:
+        return torch.empty(B, H, T, dtype=torch.float32, device=x.device).permute(0, 2, 1)
+    return torch.empty(B, T, H, dtype=torch.float32, device=x.device)
 
 
 class _FusedJointLoss(torch.autograd.Function):
@@ -88,13 +121,13 @@ class _FusedJointLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, pred, weight, bias, targets, logit_lengths, target_lengths, blank, clamp, ring_bytes,
-                skip_zero_tiles=True, save_hidden=None):
+                skip_zero_tiles=True, save_hidden=None, deterministic=None):
         L = _lib.lib()
         B, T, H = enc.shape
         U1 = pred.shape[1]
         V = weight.shape[0]
         dev = enc.device
-        enc_c = enc if enc.stride(2) == 1 and enc.stride(1) % 4 == 0 and enc.stride(0) % 4 == 0 else enc.contiguous()
+        enc_c = _kernel_layout(enc)          # no copy for the (B,H,T)-view layout of rnnt/model.py:28
         pred_c = pred.contiguous()
         weight_c = weight.contiguous()
         bias_c = bias.contiguous()
@@ -110,17 +143,21 @@ class _FusedJointLoss(torch.autograd.Function):
         fwd_bytes, _ = workspace_bytes(B, T, U1, H, V, 0, save_hidden)
         ws = torch.empty(fwd_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
+            # out-of-range lengths (torchaudio raises for them) need no sync here: the kernels clamp them and turn
+            # every cost of the batch into NaN
             _lib.check(L.rnnt_b200_joint_loss_fwd(
-                enc_c.data_ptr(), enc_c.stride(0), enc_c.stride(1), pred_c.data_ptr(), weight_c.data_ptr(),
-                bias_c.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
-                B, T, U1, H, V, blank, costs.data_ptr(), lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(),
-                beta.data_ptr(), hidden.data_ptr() if save_hidden else None, None, ws.data_ptr(), fwd_bytes,
-                _stream_ptr(dev)), "joint_loss_fwd")
+                enc_c.data_ptr(), enc_c.stride(0), enc_c.stride(1), enc_c.stride(2), pred_c.data_ptr(),
+                weight_c.data_ptr(), bias_c.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(),
+                target_lengths.data_ptr(), B, T, U1, H, V, blank, costs.data_ptr(), lp.data_ptr(), lse.data_ptr(),
+                alpha.data_ptr(), beta.data_ptr(), hidden.data_ptr() if save_hidden else None, None, ws.data_ptr(),
+                fwd_bytes, _stream_ptr(dev)), "joint_loss_fwd")
         ctx.save_for_backward(enc_c, pred_c, weight_c, bias_c, targets, logit_lengths, target_lengths,
                               lp, lse, alpha, beta, *([hidden] if save_hidden else []))
         ctx.have_hidden = save_hidden
         ctx.blank, ctx.clamp, ctx.ring_bytes = blank, clamp, ring_bytes
-        ctx.flags = 0 if skip_zero_tiles else 1
+        if deterministic is None:
+            deterministic = _DETERMINISTIC or torch.are_deterministic_algorithms_enabled()
+        ctx.flags = (0 if skip_zero_tiles else _lib.FLAG_ALL_TILES) | (_lib.FLAG_DETERMINISTIC if deterministic else 0)
         ctx.mark_non_differentiable(lp, lse, alpha, beta)
         return costs, lp, lse, alpha, beta
 
@@ -134,25 +171,35 @@ class _FusedJointLoss(torch.autograd.Function):
         V = weight.shape[0]
         dev = enc.device
         dcost = dcost.contiguous().float()
-        d_enc = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        d_enc = _grad_like(enc)
         d_pred = torch.empty(B, U1, H, dtype=torch.float32, device=dev)
-        dW = torch.empty(V, H, dtype=torch.float32, device=dev)
-        db = torch.empty(V, dtype=torch.float32, device=dev)
+        sink = _weight_grad_sink
+        event = None
+        if sink is not None and sink.accepts(V, H, dev):
+            dW, db, event = sink.weight_grad_views(V, H)     # slices of the flat all-reduce bucket
+        else:
+            sink = None
+            dW = torch.empty(V, H, dtype=torch.float32, device=dev)
+            db = torch.empty(V, dtype=torch.float32, device=dev)
         ring_tiles = pick_ring_tiles(B, T, U1, H, V, ctx.ring_bytes, ctx.have_hidden)
-        _, bwd_bytes = workspace_bytes(B, T, U1, H, V, ring_tiles, ctx.have_hidden)
+        _, bwd_bytes = workspace_bytes(B, T, U1, H, V, ring_tiles, ctx.have_hidden, ctx.flags)
         ws = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.rnnt_b200_joint_loss_bwd(
-                enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), weight.data_ptr(), bias.data_ptr(),
-                targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(), B, T, U1, H, V, ctx.blank,
-                lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
-                hidden.data_ptr() if ctx.have_hidden else None, dcost.data_ptr(), float(ctx.clamp), d_enc.data_ptr(), d_pred.data_ptr(), dW.data_ptr(), db.data_ptr(), ring_tiles,
-                ctx.flags, ws.data_ptr(), bwd_bytes, _stream_ptr(dev)), "joint_loss_bwd")
+                enc.data_ptr(), enc.stride(0), enc.stride(1), enc.stride(2), pred.data_ptr(), weight.data_ptr(),
+                bias.data_ptr(), targets.data_ptr(), logit_lengths.data_ptr(), target_lengths.data_ptr(),
+                B, T, U1, H, V, ctx.blank, lp.data_ptr(), lse.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                hidden.data_ptr() if ctx.have_hidden else None, dcost.data_ptr(), float(ctx.clamp),
+                d_enc.data_ptr(), d_enc.stride(0), d_enc.stride(1), d_enc.stride(2), d_pred.data_ptr(),
+                dW.data_ptr(), db.data_ptr(), ring_tiles, ctx.flags, event, ws.data_ptr(), bwd_bytes,
+                _stream_ptr(dev)), "joint_loss_bwd")
+            if sink is not None:
+                sink.weight_grads_enqueued()      # starts the all-reduce on its side stream, gated by the event
         if COLLECT_BACKWARD_STATS:
             global _last_backward_stats
             meta = ws[: (B + 5) * 4].view(torch.int32)     # tile table region starts at offset 0
             _last_backward_stats = torch.stack([meta[B + 4], meta[B]])
-        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None, None
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None, None, None
 
 
 def _reduce(costs, reduction):
@@ -168,7 +215,8 @@ def _reduce(costs, reduction):
 def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths, blank: int = -1,
                     clamp: float = -1, reduction: str = "mean", validate: bool = True,
                     ring_bytes: Optional[int] = None, return_residuals: bool = False,
-                    skip_zero_tiles: bool = True, save_hidden: Optional[bool] = None):
+                    skip_zero_tiles: bool = True, save_hidden: Optional[bool] = None,
+                    deterministic: Optional[bool] = None):
     """Fused replacement for `joint_ln(tanh(a.unsqueeze(2) + p.unsqueeze(1)))` (rnnt/joint.py:32-39) followed by
     `torchaudio.functional.rnnt_loss(..., blank, clamp, reduction)` (rnnt/model.py:35-41).
 
@@ -178,11 +226,15 @@ def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_length
     skip_zero_tiles=False makes the backward process every half-tile (16 t x 4 u lattice block), including those whose fp16 logit-gradients
     are identically zero (same result, more work).  save_hidden: keep the fp16 activations tanh(a+p) from the forward
     for the backward (default; the reference's autograd keeps them in fp32) or recompute them there (False: the saved
-    state shrinks to 20 bytes per lattice cell).
+    state shrinks to 20 bytes per lattice cell).  deterministic=True makes the gradients bit-identical from run to run
+    (64-bit fixed-point accumulation instead of fp32 atomics; default: RNNT_B200_DETERMINISTIC or
+    torch.use_deterministic_algorithms).  audio_frame may be the permuted (B,T,H) view of the encoder's (B,H,T) output
+    (rnnt/model.py:27-28): it is read in place, and its gradient is produced in the same layout.
+    With validate=False, lengths outside [1,T] / [0,U] (for which torchaudio raises) make every cost NaN instead.
     """
     _require_cuda(audio_frame, text_frame, weight, bias, targets, logit_lengths, target_lengths)
     if audio_frame.dtype != torch.float32 or text_frame.dtype != torch.float32:
-        raise RuntimeError("joint inputs must be float32 (the fused kernels convert to bf16 internally)")
+        raise RuntimeError("joint inputs must be float32 (the fused kernels convert to fp16 operands internally)")
     if audio_frame.dim() != 3 or text_frame.dim() != 3 or audio_frame.shape[0] != text_frame.shape[0] \
             or audio_frame.shape[2] != text_frame.shape[2] or weight.shape[1] != audio_frame.shape[2]:
         raise RuntimeError("expected audio (B,T,H), text (B,U+1,H) and weight (V,H)")
@@ -193,7 +245,8 @@ def joint_rnnt_loss(audio_frame, text_frame, weight, bias, targets, logit_length
         _validate_lengths(audio_frame.shape[1], text_frame.shape[1], logit_lengths, target_lengths)
     costs, lp, lse, alpha, beta = _FusedJointLoss.apply(audio_frame, text_frame, weight.float(), bias.float(),
                                                         targets, logit_lengths, target_lengths, int(blank),
-                                                        float(clamp), ring_bytes, bool(skip_zero_tiles), save_hidden)
+                                                        float(clamp), ring_bytes, bool(skip_zero_tiles), save_hidden,
+                                                        deterministic)
     out = _reduce(costs, reduction)
     if return_residuals:
         return out, dict(lp=lp, lse=lse, alpha=alpha, beta=beta)
@@ -356,7 +409,7 @@ def greedy_decode(audio_features, audio_feature_lens, joint_weight, joint_bias, 
             B, T, H, V, E, int(blank), max_len, int(max_outputs_per_step), tokens.data_ptr(), ntok.data_ptr(),
             margins.data_ptr() if return_margins else None, scratch.data_ptr(), _stream_ptr(dev)), "greedy_decode")
     global _last_decode_phase_cycles
-    _last_decode_phase_cycles = scratch[-64:].view(torch.int64)
+    _last_decode_phase_cycles = scratch[:64].view(torch.int64)
     n = (ntok - 1).tolist()
     toks = tokens.tolist()
     result = [toks[b][: n[b]] for b in range(B)]

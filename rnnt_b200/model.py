@@ -7,6 +7,21 @@ from .joint import JointNetwork
 from .predictor import ConvPredictor, ConvPredictorStepper
 
 
+def _is_conv_predictor(p) -> bool:
+    """ConvPredictor-shaped (rnnt/predictor.py:189-229): decided by the attributes the decode kernels read, not by class,
+    so the reference's own `rnnt.predictor.ConvPredictor` (a model built with only joint._target_ swapped) qualifies."""
+    try:
+        return all(hasattr(p, a) for a in ("embedding", "input_layer_norm", "linear", "output_layer_norm")) \
+            and hasattr(p.conv1, "conv") and hasattr(p.conv2, "conv")
+    except AttributeError:
+        return False
+
+
+def _is_lstm_predictor(p) -> bool:
+    """LSTMPredictor-shaped (rnnt/predictor.py:84-186): stateful call `p(ids, lengths, state) -> (out, lengths, state)`."""
+    return hasattr(p, "lstm_layers") and hasattr(p, "embedding")
+
+
 class RNNTModel(torch.nn.Module):
     def __init__(self, predictor, encoder, joint):
         super().__init__()
@@ -23,7 +38,8 @@ class RNNTModel(torch.nn.Module):
         prepended = torch.cat([torch.full((input_ids.shape[0], 1), blank_idx, dtype=input_ids.dtype,
                                           device=input_ids.device), input_ids], dim=1)      # model.py:20-21
         decoder_features = self.predictor(prepended)                                         # model.py:24
-        audio_features = self.encoder(mel_features).permute(0, 2, 1)                         # model.py:27-28
+        # model.py:27-28: the (N,L,C) VIEW of the encoder's (N,C,L) output goes to the kernels as is (no transposed copy)
+        audio_features = self.encoder(mel_features).permute(0, 2, 1)
         audio_feature_lens = self.encoder.calc_output_lens(mel_feature_lens)                 # model.py:29
         return self.joint.loss(audio_features, decoder_features, input_ids.int(), audio_feature_lens.int(),
                                input_id_lens.int(), blank=-1, clamp=-1, reduction="mean")
@@ -41,10 +57,15 @@ class RNNTModel(torch.nn.Module):
         kernel (`rnnt_b200_greedy_decode`); engine="graph" replays a captured CUDA graph of torch ops + the argmax
         kernel per step and checks for completion every `sync_every` steps (kept as an independent cross-check and
         for joints with audio_ln / text_ln).  The reference syncs on `.item()` every step (model.py:113)."""
-        if not isinstance(self.predictor, ConvPredictor):
-            raise ValueError("batched greedy decode supports ConvPredictor")
         if not audio_features.is_cuda:
             raise RuntimeError("rnnt_b200 decode runs on CUDA tensors only; there is no CPU fallback")
+        if _is_lstm_predictor(self.predictor):
+            if return_margins:
+                raise ValueError("return_margins is only available with a ConvPredictor")
+            return self._greedy_decode_features_stateful(audio_features, audio_feature_lens, max_length,
+                                                         max_outputs_per_step)
+        if not _is_conv_predictor(self.predictor):
+            raise ValueError("Unknown predictor type")                  # rnnt/model.py:139
         if engine == "kernel" and not hasattr(self.joint, "audio_ln") and not hasattr(self.joint, "text_ln"):
             # the whole loop (joint step, argmax, per-utterance state, incremental predictor) in one persistent kernel
             from .functional import greedy_decode
@@ -103,15 +124,51 @@ class RNNTModel(torch.nn.Module):
                         by_len.setdefault(min(len(tokens[b]), ConvPredictor.RECEPTIVE_FIELD), []).append(b)
                     for wl, group in by_len.items():
                         win = torch.tensor([tokens[b][-wl:] for b in group], dtype=torch.int64, device=dev)
-                        feats[torch.tensor(group, device=dev)] = self.predictor.last_step(win)
+                        feats[torch.tensor(group, device=dev)] = self.predictor(win)[:, -1, :]
                     active = [b for b in active if t_idx[b] < lens[b] and len(tokens[b]) < max_length]
         finally:
             self.predictor.train(was_training)
         return [tk[1:] for tk in tokens]
 
     @torch.no_grad()
+    def _greedy_decode_features_stateful(self, audio_features, audio_feature_lens, max_length: int = 200,
+                                         max_outputs_per_step: int = 10):
+        """LSTM-predictor variant (rnnt/model.py:46-87): the recurrent state lives in the predictor's own (list of
+        lists of) tensors, so the loop stays on the host, one utterance at a time as in the reference; the joint step
+        + argmax of every iteration is this repo's CUDA kernel (`JointNetwork.argmax_step`).  The reference marks the
+        LSTM predictor as unused for training; it is supported for decode parity only."""
+        dev = audio_features.device
+        blank = self.joint.blank_idx
+        lens = [int(x) for x in audio_feature_lens.tolist()]
+        was_training = self.predictor.training
+        self.predictor.eval()
+        results = []
+        try:
+            for b in range(audio_features.shape[0]):
+                tokens = [blank]
+                t, per = 0, 0
+                ids = torch.tensor([tokens], dtype=torch.int64, device=dev)
+                feats, _, state = self.predictor(ids, torch.tensor([1], dtype=torch.int64, device=dev))
+                while t < lens[b] and len(tokens) < max_length:
+                    tok = int(self.joint.argmax_step(audio_features[b, t:t + 1], feats[:, -1, :].contiguous())[0])
+                    if tok == blank or per >= max_outputs_per_step:
+                        t += 1
+                        per = 0
+                    else:
+                        tokens.append(tok)
+                        ids = torch.tensor([[tok]], dtype=torch.int64, device=dev)     # model.py:78: last token + state
+                        feats, _, state = self.predictor(ids, torch.tensor([len(tokens)], dtype=torch.int64, device=dev),
+                                                         state)
+                        per += 1
+                results.append(tokens[1:])
+        finally:
+            self.predictor.train(was_training)
+        return results
+
+    @torch.no_grad()
     def greedy_decode(self, mel_features, mel_feature_lens, max_length: int = 200):
-        """Reference signature (rnnt/model.py:130-139): batch of one, returns list[int]."""
+        """Reference signature (rnnt/model.py:130-139): batch of one, returns list[int]; dispatches on the predictor's
+        shape (ConvPredictor -> persistent kernel, LSTMPredictor -> stateful host loop), ValueError otherwise."""
         assert mel_features.shape[0] == 1, "Greedy decoding only works with a batch size of 1"
         audio_features = self.encoder(mel_features).permute(0, 2, 1).contiguous()
         # the reference loops to audio_features.shape[1] (model.py:56,100), not to the computed length

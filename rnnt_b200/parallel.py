@@ -31,6 +31,88 @@ def balanced_assignment(cells: Sequence[int], world_size: int):
     return [sorted(b) for b in buckets], loads
 
 
+class WeightGradBucket:
+    """One flat fp32 bucket for the step's weight gradients, all-reduced while the backward is still running.
+
+    Layout: [joint_ln.weight (V*H) | joint_ln.bias (V) | extra (e.g. the predictor's gradients)].  Registered with
+    `rnnt_b200.functional.set_weight_grad_sink`, the fused backward writes dW / db STRAIGHT into the first two slices
+    (no flatten / unflatten copies; autograd hands the slices to `.grad` as they are) and records a CUDA event the
+    moment they are final -- before its activation-gradient GEMM is enqueued.  `weight_grads_enqueued` then launches the
+    NCCL all-reduce of the joint slice on a side stream gated by that event, so the collective overlaps the dh GEMM
+    (DDP's bucket overlap, rnnt/train.py:67-68, for the one bucket this path owns).  `finish()` all-reduces the `extra`
+    slice (gradients that only exist after the joint's backward, e.g. the predictor's), applies the averaging and joins
+    the side stream."""
+
+    def __init__(self, V: int, H: int, extra: int, device, average: bool = True, group=None):
+        self.V, self.H, self.extra = V, H, extra
+        self.device = torch.device(device)
+        self.flat = torch.zeros(V * H + V + extra, dtype=torch.float32, device=self.device)
+        self.average, self.group = average, group
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.event = None
+        if self.stream is not None:
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(self.device))   # materialises the cudaEvent_t handle
+        self.pending = False
+        self.seconds_in_flight = 0.0
+
+    @property
+    def joint_slice(self):
+        return self.flat[: self.V * self.H + self.V]
+
+    @property
+    def extra_slice(self):
+        return self.flat[self.V * self.H + self.V:]
+
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    # ---- sink protocol used by rnnt_b200.functional._FusedJointLoss.backward
+    def accepts(self, V, H, device) -> bool:
+        return V == self.V and H == self.H and torch.device(device) == self.device
+
+    def weight_grad_views(self, V, H):
+        n = V * H
+        ev = self.event.cuda_event if self.event is not None else None
+        return self.flat[:n].view(V, H), self.flat[n:n + V], ev
+
+    def weight_grads_enqueued(self):
+        """Called right after the backward's kernels were enqueued: dW / db are final once `event` fires."""
+        if self._world() == 1:
+            return
+        if self.stream is not None:
+            self.stream.wait_event(self.event)
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.joint_slice, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(self.joint_slice, op=dist.ReduceOp.SUM, group=self.group)
+        self.pending = True
+
+    def finish(self):
+        """End of the step: all-reduce what is left (the `extra` slice; the joint slice too if no fused backward fed
+        it), average, and make the current stream wait for the result."""
+        world = self._world()
+        if world == 1:
+            return self.flat
+        cur = torch.cuda.current_stream(self.device) if self.stream is not None else None
+        if self.stream is not None:
+            self.stream.wait_stream(cur)
+            ctx = torch.cuda.stream(self.stream)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            rest = self.extra_slice if self.pending else self.flat
+            if rest.numel():
+                dist.all_reduce(rest, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                self.flat.div_(world)
+        if self.stream is not None:
+            cur.wait_stream(self.stream)
+        self.pending = False
+        return self.flat
+
+
 class GradAllReducer:
     """Flattens a fixed set of gradients into one bucket and all-reduces it (sum or average) on a side stream."""
 

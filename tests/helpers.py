@@ -7,6 +7,67 @@ import numpy as np
 import torch
 
 
+class StubEncoder(torch.nn.Module):
+    """Small stand-in for rnnt.jasper.AudioEncoder with the two members RNNTModel.forward uses (rnnt/model.py:27-29):
+    forward(mel (N,F,L)) -> (N,C,L') and calc_output_lens.  One strided Conv1d + tanh; L' = ceil(L / 2)."""
+
+    def __init__(self, n_mels: int, hidden: int):
+        super().__init__()
+        self.conv = torch.nn.Conv1d(n_mels, hidden, kernel_size=3, stride=2, padding=1)
+
+    def forward(self, mel):
+        return torch.tanh(self.conv(mel))
+
+    def calc_output_lens(self, lens):
+        return (lens + 1) // 2
+
+
+class TinyStatefulPredictor(torch.nn.Module):
+    """LSTMPredictor-shaped stand-in (rnnt/predictor.py:84-186): `p(ids, lengths, state) -> (out, lengths, state)` with
+    a `lstm_layers` list; one LSTMCell layer between an embedding and a linear + LayerNorm."""
+
+    def __init__(self, num_symbols: int, output_dim: int, dim: int):
+        super().__init__()
+        self.embedding = torch.nn.Embedding(num_symbols, dim)
+        self.lstm_layers = torch.nn.ModuleList([torch.nn.LSTMCell(dim, dim)])
+        self.linear = torch.nn.Linear(dim, output_dim)
+        self.output_layer_norm = torch.nn.LayerNorm(output_dim)
+
+    def forward(self, ids, lengths, state=None):
+        x = self.embedding(ids)                                   # (B,U,D)
+        h, c = state[0] if state is not None else (x.new_zeros(x.shape[0], x.shape[2]),) * 2
+        outs = []
+        for u in range(x.shape[1]):
+            h, c = self.lstm_layers[0](x[:, u], (h, c))
+            outs.append(h)
+        out = self.output_layer_norm(self.linear(torch.stack(outs, 1)))
+        return out, lengths, [[h, c]]
+
+
+def decode_full_setup(g):
+    """Re-create the seeded model / features of tests/golden/decode_full.npz (make_golden.py::decode_full_case) with
+    this repo's module mirrors and verify them against the stored checksums.  Returns (RNNTModel, feats, T_len)."""
+    import rnnt_b200
+    seed, n_utt, T = int(g["seed"]), int(g["n_utt"]), int(g["T"])
+    H, V, E = int(g["H"]), int(g["V"]), int(g["E"])
+    torch.manual_seed(seed)
+    joint = rnnt_b200.JointNetwork(-1, -1, H, V)
+    predictor = rnnt_b200.ConvPredictor(V, H, E, 0.3).eval()
+    with torch.no_grad():
+        joint.joint_ln.bias[V - 1] += float(g["blank_bias"])
+    gen = torch.Generator().manual_seed(seed + 1)
+    feats = torch.randn(n_utt, T, H, generator=gen)
+    T_len = torch.randint(T * 3 // 4, T + 1, (n_utt,), generator=gen)
+    T_len[0] = T
+    assert T_len.tolist() == g["T_len"].tolist()
+    cs = lambda v: float(np.abs(v.detach().numpy().astype(np.float64)).sum())
+    for k, v in predictor.state_dict().items():
+        assert cs(v) == float(g["chk." + k]), k
+    assert cs(joint.joint_ln.weight) == float(g["chk.joint_w"])
+    assert cs(feats) == float(g["chk.feats"])
+    return rnnt_b200.RNNTModel(predictor, torch.nn.Identity(), joint), feats, T_len
+
+
 def make_inputs(B, T, U, H, V, seed=1234, ragged=False, device="cuda", scale=1.0):
     g = torch.Generator().manual_seed(seed)
     enc = torch.randn(B, H, T, generator=g).permute(0, 2, 1).contiguous() * scale   # dense copy of the model.py:28 view
@@ -29,7 +90,9 @@ def make_inputs(B, T, U, H, V, seed=1234, ragged=False, device="cuda", scale=1.0
 
 def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0, save_hidden=True):
     """Call the C-ABI forward + backward directly; returns outputs plus the raw workspace and its layout.
-    save_hidden=False exercises the memory-lean mode (per-SM scratch in the forward, recomputing backward)."""
+    save_hidden=False exercises the memory-lean mode (per-SM scratch in the forward, recomputing backward).
+    flags: 1 = RNNT_B200_ALL_TILES, 2 = RNNT_B200_DETERMINISTIC.  inp["enc"] may be H-contiguous or the T-contiguous
+    permuted view of a (B,H,T) tensor; d_enc is produced in the same layout."""
     from rnnt_b200 import _lib
     from rnnt_b200.functional import _stream_ptr, pick_ring_tiles
     L = _lib.lib()
@@ -49,12 +112,13 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0, save_hidden
     hidden = torch.zeros(L.rnnt_b200_hidden_bytes(B, T, U1, H), dtype=torch.uint8, device=dev) if save_hidden else None
     hptr = hidden.data_ptr() if save_hidden else None
     f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+    d_enc = f(B, H, T).permute(0, 2, 1) if (enc.stride(1) == 1 and T > 1) else f(B, T, H)
     out = dict(costs=f(B), lp=f(B, T, U1, 2), lse=f(B, T, U1), alpha=f(B, T, U1), beta=f(B, T, U1),
-               d_enc=f(B, T, H), d_pred=f(B, U1, H), dW=f(V, H), db=f(V))
+               d_enc=d_enc, d_pred=f(B, U1, H), dW=f(V, H), db=f(V))
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     st = _stream_ptr(dev)
     _lib.check(L.rnnt_b200_joint_loss_fwd(
-        enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
+        enc.data_ptr(), enc.stride(0), enc.stride(1), enc.stride(2), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
         targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["costs"].data_ptr(),
         out["lp"].data_ptr(), out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(),
         hptr, status.data_ptr(), ws.data_ptr(), ws.numel(), st), "fwd")
@@ -62,11 +126,11 @@ def fused_raw(inp, ring_tiles=None, dcost=None, clamp=-1.0, flags=0, save_hidden
     if dcost is None:
         dcost = torch.ones(B, dtype=torch.float32, device=dev)
     _lib.check(L.rnnt_b200_joint_loss_bwd(
-        enc.data_ptr(), enc.stride(0), enc.stride(1), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
+        enc.data_ptr(), enc.stride(0), enc.stride(1), enc.stride(2), pred.data_ptr(), W.data_ptr(), b.data_ptr(),
         targets.data_ptr(), T_len.data_ptr(), U_len.data_ptr(), B, T, U1, H, V, -1, out["lp"].data_ptr(),
         out["lse"].data_ptr(), out["alpha"].data_ptr(), out["beta"].data_ptr(), hptr, dcost.data_ptr(), float(clamp),
-        out["d_enc"].data_ptr(), out["d_pred"].data_ptr(), out["dW"].data_ptr(), out["db"].data_ptr(),
-        ring_tiles, flags, ws.data_ptr(), ws.numel(), st), "bwd")
+        d_enc.data_ptr(), d_enc.stride(0), d_enc.stride(1), d_enc.stride(2), out["d_pred"].data_ptr(),
+        out["dW"].data_ptr(), out["db"].data_ptr(), ring_tiles, flags, None, ws.data_ptr(), ws.numel(), st), "bwd")
     torch.cuda.synchronize()
     meta = ws[int(offs[0]): int(offs[0]) + (B + 5) * 4].view(torch.int32)
     out.update(ws=ws, hidden=hidden, offs=[int(x) for x in offs], Hp=hp.value, Vp=vp.value, ring_tiles=ring_tiles,

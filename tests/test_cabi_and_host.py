@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(handle, s), s
     assert set(syms) == set(_lib.EXPORTED_SYMBOLS)
-    assert handle.rnnt_b200_abi_version() == 2
+    assert handle.rnnt_b200_abi_version() == 3
 
 
 def test_ctypes_signatures_match_the_header_prototypes():
@@ -48,15 +48,15 @@ def test_argument_validation_without_gpu():
     L = _lib.lib()
     assert L.rnnt_b200_max_tiles(32, 400, 101) == 32 * 25 * 13
     fwd, bwd = C.c_size_t(0), C.c_size_t(0)
-    assert L.rnnt_b200_workspace_bytes(32, 400, 101, 1024, 1024, 2080, 0, C.byref(fwd), C.byref(bwd)) == 0
+    assert L.rnnt_b200_workspace_bytes(32, 400, 101, 1024, 1024, 2080, 0, 0, C.byref(fwd), C.byref(bwd)) == 0
     assert fwd.value >= 1024 * 1024 * 2 and bwd.value >= 2080 * 128 * 2048 * 2
-    assert L.rnnt_b200_workspace_bytes(0, 400, 101, 1024, 1024, 1, 0, C.byref(fwd), C.byref(bwd)) < 0
+    assert L.rnnt_b200_workspace_bytes(0, 400, 101, 1024, 1024, 1, 0, 0, C.byref(fwd), C.byref(bwd)) < 0
     assert b"invalid shape" in L.rnnt_b200_last_error()
     # invalid arguments are rejected before anything touches a device
-    rc = L.rnnt_b200_joint_loss_fwd(None, 0, 0, None, None, None, None, None, None, 2, 8, 3, 12, 16, -1,
+    rc = L.rnnt_b200_joint_loss_fwd(None, 0, 0, 1, None, None, None, None, None, None, 2, 8, 3, 12, 16, -1,
                                     None, None, None, None, None, None, None, None, 0, None)
     assert rc == -2 and b"multiple of 8" in L.rnnt_b200_last_error()
-    rc = L.rnnt_b200_joint_loss_fwd(None, 0, 0, None, None, None, None, None, None, 2, 8, 3000, 16, 16, -1,
+    rc = L.rnnt_b200_joint_loss_fwd(None, 0, 0, 1, None, None, None, None, None, None, 2, 8, 3000, 16, 16, -1,
                                     None, None, None, None, None, None, None, None, 0, None)
     assert L.rnnt_b200_hidden_bytes(32, 400, 101, 1024) == 32 * 25 * 13 * 128 * 1024 * 2
     assert rc == -5

@@ -1,9 +1,10 @@
 """GPU parity tests (-m gpu): the CUDA path, called through the C-ABI / public API, against the oracle.
 
 Tolerances (stated once):
-  * per-utterance loss: relative 1e-4 vs the fp32 reference (north_star bar), bf16 tensor-core GEMM inside;
-  * gradients (fp16 activations/weights, bf16 logit-gradients, fp32 accumulation): relative Frobenius error
-    <= 2e-2 vs the fp32 reference and <= 6e-3 vs a reference whose joint GEMM operands are rounded to fp16;
+  * per-utterance loss: relative 1e-4 vs the fp32 reference (north_star bar); fp16-operand tensor-core GEMM inside;
+  * gradients (fp16 activations / weights / logit-gradients, fp32 accumulation): relative Frobenius error <= 2e-3 vs the
+    fp32 reference and <= 1e-3 vs a reference whose joint GEMM operands are rounded to fp16 (measured at H=V=1024:
+    2.5e-4 / 1.5e-4; the same path run by torch in bf16 is ~10x worse -- test_full_size_vs_reference prints both);
   * lattice / dense-logits kernels (fp32 throughout): 1e-5 relative;  decode tokens: exact.
 """
 import os
@@ -17,8 +18,9 @@ from helpers import fused_raw, make_inputs, rel_err, torch_reference
 pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 1e-4
-GRAD_TOL_FP32 = 2e-2
-GRAD_TOL_BF16 = 6e-3
+GRAD_TOL_FP32 = 2e-3     # vs the fp32 reference
+GRAD_TOL_F16 = 1e-3      # vs a reference whose GEMM operands are rounded to fp16 like the kernels' (isolates kernel bugs)
+GRAD_TOL_TINY = 6e-3     # shapes with H < 64: a handful of products per logit, fp16 rounding does not average out
 
 
 def _golden(golden_dir, name):
@@ -55,7 +57,7 @@ def test_fused_vs_oracle_same_device(shape):
     assert (out["costs"] - ref["costs"]).abs().max() <= LOSS_RTOL * ref["costs"].abs().max()
     for k in ("d_enc", "d_pred", "dW", "db"):
         assert rel_err(out[k], ref[k])[0] <= GRAD_TOL_FP32, (k, rel_err(out[k], ref[k]))
-        assert rel_err(out[k], refq[k])[0] <= GRAD_TOL_BF16, (k, rel_err(out[k], refq[k]))
+        assert rel_err(out[k], refq[k])[0] <= GRAD_TOL_F16, (k, rel_err(out[k], refq[k]))
 
 
 def test_fuzz_small_ragged_shapes_vs_cpu_reference():
@@ -256,21 +258,6 @@ def test_error_behaviour_mirrors_torchaudio():
     with pytest.raises(RuntimeError, match="logits must be contiguous"):
         rnnt_b200.rnnt_loss(logits.transpose(1, 2).contiguous().transpose(1, 2), inp["targets"], inp["T_len"],
                             inp["U_len"])
-
-
-def test_strided_encoder_view_is_accepted():
-    """audio_frame arrives as a (B,T,H) permuted view of (B,H,T) (rnnt/model.py:28)."""
-    import rnnt_b200
-    inp = make_inputs(2, 16, 5, 64, 256)
-    enc_bht = inp["enc"].permute(0, 2, 1).contiguous()
-    view = enc_bht.permute(0, 2, 1).requires_grad_(True)
-    assert not view.is_contiguous()
-    a = rnnt_b200.joint_rnnt_loss(view, inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"])
-    b = rnnt_b200.joint_rnnt_loss(inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"],
-                                  inp["U_len"])
-    assert float(a.detach()) == float(b.detach())
-    a.backward()
-    assert view.grad.shape == view.shape
 
 
 def test_joint_module_dropin_and_zero_edit_mode():
@@ -492,3 +479,285 @@ def test_two_gpu_gradient_allreduce_nccl(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ------------------------------------------------------------------------------------------------ round 2 additions
+def _bf16_torch_baseline(inp):
+    """The same path as torch would run it in bf16 (activations and weights rounded to bf16, bf16 matmul with fp32
+    accumulation, bf16 logits) -- only used to put this repo's gradient error into scale."""
+    import torchaudio
+    enc = inp["enc"].detach().clone().requires_grad_(True)
+    pred = inp["pred"].detach().clone().requires_grad_(True)
+    W = inp["W"].detach().clone().requires_grad_(True)
+    b = inp["b"].detach().clone().requires_grad_(True)
+    h = torch.tanh(enc.unsqueeze(2) + pred.unsqueeze(1)).to(torch.bfloat16)
+    logits = torch.nn.functional.linear(h, W.to(torch.bfloat16), b.to(torch.bfloat16)).float()
+    costs = torchaudio.functional.rnnt_loss(logits, inp["targets"], inp["T_len"], inp["U_len"], blank=-1, clamp=-1,
+                                            reduction="none")
+    costs.sum().backward()
+    return dict(costs=costs.detach(), d_enc=enc.grad, d_pred=pred.grad, dW=W.grad, db=b.grad)
+
+
+def test_full_size_vs_reference(capsys):
+    """BASELINE configs[1] at FULL size (B=32,T=400,U=100,H=V=1024): the public API, fed the permuted (B,H,T) encoder
+    view that rnnt/model.py:28 produces, against the reference's own call path (torch fp32 linear+tanh + torchaudio
+    rnnt_loss, ~20 GiB) on the same GPU.  Also reports the error a bf16 torch run of the same path makes."""
+    import rnnt_b200
+    B, T, U, H, V = 32, 400, 100, 1024, 1024
+    inp = make_inputs(B, T, U, H, V, ragged=False, seed=2026)
+    ref = torch_reference(inp)
+    ref = {k: v for k, v in ref.items() if k != "logits"}
+    torch.cuda.empty_cache()
+    enc_bht = inp["enc"].permute(0, 2, 1).contiguous()
+    view = enc_bht.permute(0, 2, 1).requires_grad_(True)            # (B,T,H) view, T-contiguous
+    pred = inp["pred"].clone().requires_grad_(True)
+    W = inp["W"].clone().requires_grad_(True)
+    b = inp["b"].clone().requires_grad_(True)
+    costs = rnnt_b200.joint_rnnt_loss(view, pred, W, b, inp["targets"], inp["T_len"], inp["U_len"], reduction="none")
+    costs.sum().backward()
+    ours = dict(costs=costs.detach(), d_enc=view.grad, d_pred=pred.grad, dW=W.grad, db=b.grad)
+    cost_rel = float(((ours["costs"] - ref["costs"]).abs() / ref["costs"].abs()).max())
+    assert cost_rel <= LOSS_RTOL, cost_rel
+    errs = {k: rel_err(ours[k], ref[k])[0] for k in ("d_enc", "d_pred", "dW", "db")}
+    for k, e in errs.items():
+        assert e <= GRAD_TOL_FP32, (k, e)
+    del costs, view, pred, W, b
+    torch.cuda.empty_cache()
+    small = {k: (v[:8].contiguous() if k in ("enc", "pred", "targets", "T_len", "U_len") else v) for k, v in inp.items()}
+    ref8, bf8 = torch_reference(small), _bf16_torch_baseline(small)
+    bf_errs = {k: rel_err(bf8[k], ref8[k])[0] for k in ("d_enc", "d_pred", "dW", "db")}
+    bf_cost = float(((bf8["costs"] - ref8["costs"]).abs() / ref8["costs"].abs()).max())
+    with capsys.disabled():
+        print(f"\n[full-size parity] cost rel err: ours {cost_rel:.2e} (bar 1e-4), bf16 torch {bf_cost:.2e}")
+        for k in errs:
+            print(f"[full-size parity] {k}: rel-Frobenius ours {errs[k]:.2e}  bf16 torch (B=8 slice) {bf_errs[k]:.2e}")
+    for k in errs:
+        assert errs[k] < bf_errs[k], (k, errs[k], bf_errs[k])      # fp16 operands beat the bf16 torch baseline
+
+
+def test_trained_scale_inputs_stay_in_fp16_range():
+    """Large-magnitude activations (|enc|, |pred| ~ 4 sigma = 16) and weights up to |W| ~ 1 (32x the init range), i.e. a
+    sharp, trained-looking softmax: fp16 operands (tanh in [-1,1], W, S-scaled gradients) must not overflow or lose
+    the loss / gradient parity."""
+    B, T, U, H, V = 2, 60, 20, 1024, 1024
+    inp = make_inputs(B, T, U, H, V, ragged=True, seed=77, scale=4.0)
+    inp["W"] = inp["W"] * 32.0
+    inp["b"] = inp["b"] * 32.0
+    ref = torch_reference(inp)
+    out = fused_raw(inp)
+    assert torch.isfinite(out["costs"]).all()
+    assert ((out["costs"] - ref["costs"]).abs() <= LOSS_RTOL * ref["costs"].abs()).all(), (out["costs"], ref["costs"])
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert torch.isfinite(out[k]).all()
+        assert rel_err(out[k], ref[k])[0] <= GRAD_TOL_FP32, (k, rel_err(out[k], ref[k]))
+
+
+def test_strided_encoder_view_is_read_in_place():
+    """f-2: the (B,T,H) view of the encoder's (B,H,T) output (rnnt/model.py:27-28) is consumed without a transposed copy
+    (the tensor saved for the backward IS the view), gives bit-identical costs, and its gradient comes back in the
+    encoder's own layout."""
+    import rnnt_b200
+    for (B, T, U, H, V) in [(2, 16, 5, 64, 256), (3, 37, 9, 72, 300), (2, 50, 12, 128, 256), (1, 33, 4, 64, 64)]:
+        inp = make_inputs(B, T, U, H, V, ragged=True, seed=3)
+        enc_bht = inp["enc"].permute(0, 2, 1).contiguous()
+        view = enc_bht.permute(0, 2, 1).requires_grad_(True)
+        assert not view.is_contiguous() or T == 1
+        dense = inp["enc"].clone().requires_grad_(True)
+        args = (inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"])
+        a = rnnt_b200.joint_rnnt_loss(view, *args, reduction="none")
+        b = rnnt_b200.joint_rnnt_loss(dense, *args, reduction="none")
+        saved = a.grad_fn.saved_tensors[0]
+        assert saved.data_ptr() == view.data_ptr() and saved.stride() == view.stride()
+        assert torch.equal(a.detach(), b.detach())
+        a.sum().backward(); b.sum().backward()
+        assert view.grad.shape == view.shape
+        assert rel_err(view.grad, dense.grad)[0] < 1e-5, (B, T, U, H, V)
+        out_view = fused_raw(dict(inp, enc=view.detach()))
+        assert out_view["d_enc"].stride(1) == 1 or T == 1                       # gradient in (B,H,T) memory order
+        assert rel_err(out_view["d_enc"], dense.grad)[0] < 1e-5
+        for b_ in range(B):
+            assert not out_view["d_enc"][b_, int(inp["T_len"][b_]):].any()
+
+
+def test_deterministic_mode_is_bit_identical():
+    """RNNT_B200_DETERMINISTIC: cross-CTA sums in 64-bit fixed point -> gradients identical bit for bit from run to run
+    (the default mode uses fp32 atomics, whose order varies), and equal to the default mode up to fp32 rounding."""
+    inp = make_inputs(4, 120, 30, 256, 512, ragged=True, seed=21)
+    a = fused_raw(inp, flags=2)
+    b = fused_raw(inp, flags=2)
+    d = fused_raw(inp, flags=0)
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        assert torch.equal(a[k], b[k]), k
+        assert rel_err(a[k], d[k])[0] < 1e-5, (k, rel_err(a[k], d[k]))
+    view = inp["enc"].permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    c = fused_raw(dict(inp, enc=view), flags=2)
+    assert torch.equal(c["d_enc"], a["d_enc"]) and torch.equal(c["dW"], a["dW"])
+    import rnnt_b200
+    enc = inp["enc"].clone().requires_grad_(True)
+    g = []
+    for _ in range(2):
+        enc.grad = None
+        rnnt_b200.joint_rnnt_loss(enc, inp["pred"], inp["W"], inp["b"], inp["targets"], inp["T_len"], inp["U_len"],
+                                  deterministic=True).backward()
+        g.append(enc.grad.clone())
+    assert torch.equal(g[0], g[1])
+
+
+def test_out_of_range_lengths_poison_the_costs():
+    """validate=False skips the host-side checks (no sync); lengths torchaudio would raise for must not pass silently:
+    the kernels clamp them (no out-of-bounds access) and every cost of the batch becomes NaN."""
+    import rnnt_b200
+    inp = make_inputs(3, 12, 5, 64, 256, seed=9)
+    args = (inp["enc"], inp["pred"], inp["W"], inp["b"], inp["targets"])
+    ok = rnnt_b200.joint_rnnt_loss(*args, inp["T_len"], inp["U_len"], reduction="none", validate=False)
+    assert torch.isfinite(ok).all()
+    for bad_T, bad_U in ((torch.tensor([12, 13, 12]), None), (torch.tensor([12, 0, 12]), None),
+                         (None, torch.tensor([5, 9, 5])), (None, torch.tensor([5, -1, 5]))):
+        tl = inp["T_len"] if bad_T is None else bad_T.int().cuda()
+        ul = inp["U_len"] if bad_U is None else bad_U.int().cuda()
+        out = rnnt_b200.joint_rnnt_loss(*args, tl, ul, reduction="none", validate=False)
+        assert torch.isnan(out).all(), (tl, ul, out)
+    out = fused_raw(dict(inp, T_len=torch.tensor([12, 40, 12], dtype=torch.int32, device="cuda")))
+    assert out["status"] == 1 and torch.isnan(out["costs"]).all()
+
+
+def test_preprojection_joint_matches_reference_golden(golden_dir):
+    """f-4: JointNetwork with audio_ln / text_ln (rnnt/joint.py:8-12,26-30) -- costs and every gradient, including the
+    projections' weights and the raw (unprojected) inputs, against vectors produced by the reference module."""
+    import rnnt_b200
+    g = np.load(os.path.join(golden_dir, "loss_proj.npz"))
+    Fa, Ft = g["audio"].shape[2], g["text"].shape[2]
+    V, H = g["param.joint_ln.weight"].shape
+    joint = rnnt_b200.JointNetwork(Fa, Ft, H, V)
+    joint.load_state_dict({k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")})
+    joint = joint.cuda()
+    audio = torch.from_numpy(g["audio"]).cuda().requires_grad_(True)
+    text = torch.from_numpy(g["text"]).cuda().requires_grad_(True)
+    t = lambda k: torch.from_numpy(g[k]).to(torch.int32).cuda()
+    costs = joint.loss(audio, text, t("targets"), t("T_len"), t("U_len"), reduction="none")
+    costs.sum().backward()
+    assert np.abs(costs.detach().cpu().numpy() - g["costs"]).max() <= LOSS_RTOL * np.abs(g["costs"]).max()
+    assert rel_err(audio.grad.cpu(), torch.from_numpy(g["d_audio"]))[0] <= GRAD_TOL_TINY
+    assert rel_err(text.grad.cpu(), torch.from_numpy(g["d_text"]))[0] <= GRAD_TOL_TINY
+    for name, p in joint.named_parameters():
+        assert rel_err(p.grad.cpu(), torch.from_numpy(g["grad." + name]))[0] <= GRAD_TOL_TINY, name
+
+
+def test_model_forward_matches_reference_golden(golden_dir):
+    """a-7: RNNTModel.forward end to end (the call train.py:133 makes) against the reference's RNNTModel.forward
+    (rnnt/model.py:17-43): blank prepend, predictor, encoder + permuted view, calc_output_lens, .int() casts, mean loss,
+    and the gradients autograd carries back into joint, predictor and encoder."""
+    import rnnt_b200
+    from helpers import StubEncoder
+    g = np.load(os.path.join(golden_dir, "model_forward.npz"))
+    V, H = g["param.joint.joint_ln.weight"].shape
+    E = g["param.predictor.embedding.weight"].shape[1]
+    n_mels = g["mel"].shape[1]
+    model = rnnt_b200.RNNTModel(rnnt_b200.ConvPredictor(V, H, E, 0.0), StubEncoder(n_mels, H),
+                                rnnt_b200.JointNetwork(-1, -1, H, V))
+    model.load_state_dict({k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")})
+    model = model.cuda().train()
+    loss = model(torch.from_numpy(g["mel"]).cuda(), torch.from_numpy(g["mel_lens"]).cuda(),
+                 torch.from_numpy(g["input_ids"]).cuda(), torch.from_numpy(g["id_lens"]).cuda(), blank_idx=V - 1)
+    assert loss.dim() == 0
+    assert abs(float(loss.detach()) - float(g["loss"])) <= LOSS_RTOL * abs(float(g["loss"]))
+    loss.backward()
+    for name, p in model.named_parameters():
+        want = torch.from_numpy(g["grad." + name])
+        assert p.grad is not None, name
+        r, a = rel_err(p.grad.cpu(), want)
+        assert r <= GRAD_TOL_TINY or a < 1e-6, (name, r, a)
+
+
+def test_greedy_decode_full_size_matches_reference_golden(golden_dir):
+    """BASELINE configs[4] width (H=V=1024, E=512, T up to 400, max_length 200): tokens of the persistent decode kernel
+    against the reference's own loop (rnnt/model.py:90-128, fp32 CPU), for 12 seeded utterances.  The weights and
+    features are re-created from the stored seed (checksums verified).  Decisions whose reference top-2 gap is below
+    1e-4 may legitimately depend on fp32 summation order, so exactness is required up to the first such decision of
+    an utterance (its position is stored in the fixture) and for whole utterances without one."""
+    import rnnt_b200
+    from helpers import decode_full_setup
+    g = np.load(os.path.join(golden_dir, "decode_full.npz"))
+    model, feats, T_len = decode_full_setup(g)
+    model = model.cuda().eval()
+    got, margins = model.greedy_decode_features(feats.cuda(), T_len, max_length=int(g["max_length"]),
+                                                return_margins=True)
+    off, exact = 0, 0
+    for i, n in enumerate(g["tok_len"]):
+        want = g["tok_flat"][off:off + n].tolist()
+        off += n
+        safe = int(g["safe_len"][i])
+        assert got[i][:safe] == want[:safe], (i, safe, min(margins[i]))
+        if safe == n:
+            assert got[i] == want, (i, min(margins[i]))
+            exact += 1
+    assert exact >= 8                                   # at least 8 utterances are pinned token for token
+
+
+def test_decode_single_utterance_odd_vocab():
+    """B = 1 with an odd vocabulary (the reference-signature greedy_decode case): scratch regions stay aligned."""
+    import rnnt_b200
+    torch.manual_seed(3)
+    H, V, E = 64, 29, 32
+    joint = rnnt_b200.JointNetwork(-1, -1, H, V)
+    with torch.no_grad():
+        joint.joint_ln.weight.mul_(3.0)
+        joint.joint_ln.bias[V - 1] += 2.0
+    model = rnnt_b200.RNNTModel(rnnt_b200.ConvPredictor(V, H, E, 0.3), torch.nn.Identity(), joint).cuda().eval()
+    feats = torch.randn(1, 30, H, device="cuda")
+    lens = torch.tensor([30])
+    got = model.greedy_decode_features(feats, lens, max_length=40)
+    assert got == model._greedy_decode_features_hostloop(feats, lens, max_length=40)
+    assert got == model.greedy_decode_features(feats, lens, max_length=40, engine="graph")
+    assert rnnt_b200.functional._last_decode_phase_cycles is not None
+
+
+def test_greedy_decode_dispatches_on_predictor_shape():
+    """RNNTModel.greedy_decode (rnnt/model.py:130-139) accepts any ConvPredictor-SHAPED module (e.g. the reference's own
+    class when only joint._target_ is swapped), runs LSTMPredictor-shaped ones through the stateful loop
+    (rnnt/model.py:46-87) and raises the reference's ValueError otherwise."""
+    import rnnt_b200
+    from helpers import TinyStatefulPredictor
+    torch.manual_seed(5)
+    H, V, E = 64, 32, 32
+    joint = rnnt_b200.JointNetwork(-1, -1, H, V)
+    with torch.no_grad():
+        joint.joint_ln.weight.mul_(3.0)
+        joint.joint_ln.bias[V - 1] += 1.5
+
+    class Wrapped(torch.nn.Module):                     # not a rnnt_b200.ConvPredictor instance, same attributes
+        def __init__(self, inner):
+            super().__init__()
+            for name in ("embedding", "input_layer_norm", "conv1", "conv2", "linear", "output_layer_norm"):
+                setattr(self, name, getattr(inner, name))
+            self.inner = inner
+
+        def forward(self, ids):
+            return self.inner(ids)
+
+    conv = rnnt_b200.ConvPredictor(V, H, E, 0.3)
+    feats = torch.randn(2, 20, H, device="cuda")
+    lens = torch.tensor([20, 13])
+    a = rnnt_b200.RNNTModel(conv, torch.nn.Identity(), joint).cuda().eval().greedy_decode_features(feats, lens, 30)
+    b = rnnt_b200.RNNTModel(Wrapped(conv), torch.nn.Identity(), joint).cuda().eval().greedy_decode_features(feats, lens, 30)
+    assert a == b and sum(len(x) for x in a) > 0
+    # stateful (LSTM-shaped) predictor: this repo's joint kernel inside the reference's loop vs plain torch
+    lstm = TinyStatefulPredictor(V, H, E)
+    model = rnnt_b200.RNNTModel(lstm, torch.nn.Identity(), joint).cuda().eval()
+    got = model.greedy_decode_features(feats, lens, 30)
+    for i in range(2):
+        tokens, t, per = [V - 1], 0, 0
+        f, _, st = lstm(torch.tensor([tokens], device="cuda"), torch.tensor([1], device="cuda"))
+        while t < int(lens[i]) and len(tokens) < 30:
+            tok = int(joint.single_forward(feats[i, t:t + 1], f[:, -1, :]).argmax(-1))
+            if tok == V - 1 or per >= 10:
+                t += 1; per = 0
+            else:
+                tokens.append(tok)
+                f, _, st = lstm(torch.tensor([[tok]], device="cuda"), torch.tensor([len(tokens)], device="cuda"), st)
+                per += 1
+        assert got[i] == tokens[1:], i
+    one = model.greedy_decode(feats[:1].permute(0, 2, 1), torch.tensor([20]), max_length=30)
+    assert one == got[0]
+    with pytest.raises(ValueError, match="Unknown predictor type"):
+        rnnt_b200.RNNTModel(torch.nn.Linear(2, 2), torch.nn.Identity(), joint).cuda().greedy_decode_features(feats, lens)

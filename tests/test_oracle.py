@@ -80,3 +80,64 @@ def test_oracle_greedy_decode_matches_reference(golden_dir):
         got, margins = orc.greedy_decode(g["feats"][i], int(g["T_len"][i]), g["W"], g["b"], sd, blank=V - 1,
                                          max_length=int(g["max_length"]))
         assert got == want, (i, min(margins))
+
+
+def test_oracle_preprojection_joint_matches_reference(golden_dir):
+    """audio_ln / text_ln variant (rnnt/joint.py:8-12,26-30), vectors from the reference module."""
+    g = _load(golden_dir, "loss_proj")
+    P = lambda k: g["param." + k]
+    out = orc.loss_and_grads(g["audio"], g["text"], P("joint_ln.weight"), P("joint_ln.bias"), g["targets"], g["T_len"],
+                             g["U_len"], blank=-1, audio_ln=(P("audio_ln.weight"), P("audio_ln.bias")),
+                             text_ln=(P("text_ln.weight"), P("text_ln.bias")))
+    np.testing.assert_allclose(out["costs"], g["costs"], rtol=2e-6, atol=2e-5)
+    pairs = [("d_enc", "d_audio"), ("d_pred", "d_text"), ("dW", "grad.joint_ln.weight"), ("db", "grad.joint_ln.bias"),
+             ("dWa", "grad.audio_ln.weight"), ("dba", "grad.audio_ln.bias"), ("dWt", "grad.text_ln.weight"),
+             ("dbt", "grad.text_ln.bias")]
+    for mine, ref in pairs:
+        err = np.abs(out[mine] - g[ref]).max()
+        assert err <= 1e-4 * max(1.0, np.abs(g[ref]).max()), (mine, err)
+
+
+def test_oracle_model_forward_glue_matches_reference(golden_dir):
+    """rnnt/model.py:17-43: blank prepend (:20-21), permuted encoder view (:28), calc_output_lens (:29), .int() casts
+    (:36-38), reduction="mean".  Encoder / predictor features come from this repo's module mirrors loaded with the
+    golden parameters; the oracle supplies joint + loss; the scalar must equal the reference's."""
+    import torch
+    import rnnt_b200
+    from helpers import StubEncoder
+    g = _load(golden_dir, "model_forward")
+    V, H = g["param.joint.joint_ln.weight"].shape
+    E = g["param.predictor.embedding.weight"].shape[1]
+    pred_m = rnnt_b200.ConvPredictor(V, H, E, 0.0)
+    pred_m.load_state_dict({k[16:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.predictor.")})
+    enc_m = StubEncoder(g["mel"].shape[1], H)
+    enc_m.load_state_dict({k[14:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.encoder.")})
+    ids = torch.from_numpy(g["input_ids"])
+    with torch.no_grad():
+        prepended = torch.cat([torch.full((ids.shape[0], 1), V - 1, dtype=ids.dtype), ids], 1)
+        dec = pred_m(prepended).numpy()
+        audio = enc_m(torch.from_numpy(g["mel"])).permute(0, 2, 1).numpy()
+        lens = enc_m.calc_output_lens(torch.from_numpy(g["mel_lens"])).numpy()
+    out = orc.loss_and_grads(audio, dec, g["param.joint.joint_ln.weight"], g["param.joint.joint_ln.bias"],
+                             g["input_ids"].astype(np.int32), lens, g["id_lens"], blank=-1)
+    assert abs(out["costs"].mean() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+def test_oracle_greedy_decode_full_width_matches_reference(golden_dir):
+    """H = V = 1024, E = 512 (BASELINE configs[4] width): the fp64 oracle loop reproduces the reference's tokens up to the
+    first near-tie (top-2 gap < 1e-4) of each utterance.  Three utterances (the fp64 full re-run is slow)."""
+    from helpers import decode_full_setup
+    g = _load(golden_dir, "decode_full")
+    model, feats, T_len = decode_full_setup(g)
+    sd = {k: v.numpy() for k, v in model.predictor.state_dict().items()}
+    W = model.joint.joint_ln.weight.detach().numpy()
+    b = model.joint.joint_ln.bias.detach().numpy()
+    offs = np.concatenate([[0], np.cumsum(g["tok_len"])])
+    for i in (3, 7, 1):
+        want = g["tok_flat"][offs[i]:offs[i + 1]].tolist()
+        got, margins = orc.greedy_decode(feats[i].numpy(), int(T_len[i]), W, b, sd, blank=int(g["V"]) - 1,
+                                         max_length=int(g["max_length"]))
+        safe = int(g["safe_len"][i])
+        assert got[:safe] == want[:safe], (i, min(margins))
+        if safe == len(want):
+            assert got == want
