@@ -3,14 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one fused joint+loss forward AND backward over one synthetic batch (per GPU: B=32, T=400, U=100,
-H=1024, V=1024 -- BASELINE.json configs[1]); with N>1 (launched by torchrun, one rank per GPU) every rank
-processes its own B=32 utterances (global batch 32*N, no data-path collective) and the step ends with one NCCL
-all-reduce of the joint + predictor weight gradients (4,200,448 fp32).  Rank 0 prints ONE JSON line.
+One "step" = one fused joint+loss forward AND backward over one synthetic batch.
+  N = 1: B=32, T=400, U=100, H=1024, V=1024 -- BASELINE.json configs[1], the configuration the metric is quoted on.
+  N > 1 (launched by torchrun, one rank per GPU): BASELINE.json configs[2] -- a GLOBAL batch of 256 utterances sharded
+         by utterance (256/N per GPU, one launch per rank, no data-path collective; strong scaling); the weight
+         gradients land directly in one flat bucket and their NCCL all-reduce (joint 1,049,600 + predictor
+         3,150,848 fp32) starts as soon as dW/db are final, overlapping the activation-gradient GEMM.
+         `--global-batch 0` selects the round-1 weak-scaling workload (B=32 per GPU) instead.
+The encoder features are handed over as the reference does (rnnt/model.py:27-28): a (B,T,H) VIEW of a (B,H,T) tensor.
+Rank 0 prints ONE JSON line.
 
 `--impl reference` times the reference's own CPU implementation of the path (torch nn.functional.linear + tanh +
 torchaudio.functional.rnnt_loss forward+backward, i.e. rnnt/joint.py:25-39 + rnnt/model.py:35-41 restated in
-oracle/ref_path.py) on the box's host cores, on a bounded sample of the same workload.
+oracle/ref_path.py) on the box's host cores, on BASELINE.json configs[0] (B=4,T=200,U=40), the reference's own
+CPU-runnable case.
 """
 from __future__ import annotations
 
@@ -32,17 +38,21 @@ UNIT = "lattice-cells/s"
 B, T, U, H, V = 32, 400, 100, 1024, 1024
 PRED_GRAD_ELEMS = 3_150_848        # ConvPredictor parameters that ride the same all-reduce
 FLOP_PER_CELL_GEMM = 2 * H * V     # one H x V contraction per lattice cell
-CPU_SAMPLE = dict(B=2, T=400, U=100)
+CPU_SAMPLE = dict(B=4, T=200, U=40)   # BASELINE.json configs[0] / BASELINE.md section 4
+GLOBAL_BATCH = 256                    # BASELINE.json configs[2]
 
 
 def load_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) -- burst for short timed regions, sustained for
+    seconds-long loops under the power cap -- else the fallback B200_PROFILING.md states."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(tflops=float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0))),
-                    hbm=float(p.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(tflops=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+        burst = float(p.get("bf16_tflops", 1590.0))
+        return dict(burst=burst, sustained=float(p.get("bf16_tflops_sustained", burst)),
+                    hbm=float(p.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -103,9 +113,11 @@ class ClockSampler:
                     samples=len(self.samples), reasons=reasons)
 
 
-def synth_inputs(torch, seed, device, b=B, t=T, u=U, pin=False):
+def synth_inputs(torch, seed, device, b=B, t=T, u=U, pin=False, view=True):
+    """Synthetic batch.  view=True: enc is generated as the encoder would deliver it, a (B,H,T) tensor, and
+    handed over as its (B,T,H) permuted view (rnnt/model.py:28) -- the kernels read that layout in place."""
     g = torch.Generator().manual_seed(seed)
-    enc = torch.randn(b, t, H, generator=g)
+    enc = torch.randn(b, H, t, generator=g) if view else torch.randn(b, t, H, generator=g)
     pred = torch.randn(b, u + 1, H, generator=g)
     bound = 1.0 / (H ** 0.5)
     W = (torch.rand(V, H, generator=g) * 2 - 1) * bound
@@ -114,9 +126,10 @@ def synth_inputs(torch, seed, device, b=B, t=T, u=U, pin=False):
     T_len = torch.full((b,), t, dtype=torch.int32)
     U_len = torch.full((b,), u, dtype=torch.int32)
     d = dict(enc=enc, pred=pred, W=W, b=bias, targets=targets, T_len=T_len, U_len=U_len)
-    if pin:
-        return {k: v.pin_memory() for k, v in d.items()}
-    return {k: v.to(device) for k, v in d.items()}
+    d = {k: v.pin_memory() for k, v in d.items()} if pin else {k: v.to(device) for k, v in d.items()}
+    if view:
+        d["enc"] = d["enc"].permute(0, 2, 1)
+    return d
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -126,22 +139,39 @@ def cpu_reference_step(torch, inp):
                               inp["U_len"], reduction="mean")
 
 
-def time_cpu_reference(steps, warmup):
+def time_cpu_reference(steps, warmup, one_thread_too=True):
+    """The reference path on the host cores, BASELINE.md section 4: B=4,T=200,U=40, fp32, all threads (best of `steps`
+    after `warmup`) and -- once -- a single thread.  ~10-25 s of CPU work in total."""
     import torch
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    inp = synth_inputs(torch, 1234, "cpu", **{k.lower(): v for k, v in CPU_SAMPLE.items()})
+    inp = synth_inputs(torch, 1234, "cpu", view=False, **{k.lower(): v for k, v in CPU_SAMPLE.items()})
     cells = CPU_SAMPLE["B"] * CPU_SAMPLE["T"] * (CPU_SAMPLE["U"] + 1)
-    for _ in range(warmup):
-        cpu_reference_step(torch, inp)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_reference_step(torch, inp)
-    dt = (time.perf_counter() - t0) / max(1, steps)
-    return dict(value=cells / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"B={CPU_SAMPLE['B']},T={CPU_SAMPLE['T']},U={CPU_SAMPLE['U']},H={H},V={V} fp32, "
-                       f"torch {torch.__version__} linear+tanh + torchaudio rnnt_loss fwd+bwd, {steps} timed step(s) "
-                       f"of {cells} cells, {dt:.2f} s/step"), dt
+
+    def best_of(n, w):
+        for _ in range(w):
+            cpu_reference_step(torch, inp)
+        best = float("inf")
+        for _ in range(n):
+            t0 = time.perf_counter()
+            cpu_reference_step(torch, inp)
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    torch.set_num_threads(cores)
+    dt = best_of(max(1, steps), warmup)
+    one = None
+    if one_thread_too:
+        torch.set_num_threads(1)
+        one = best_of(1, 0)
+        torch.set_num_threads(cores)
+    out = dict(value=cells / dt, unit=UNIT, cores=cores, kind="port",
+               sample=f"BASELINE configs[0]: B={CPU_SAMPLE['B']},T={CPU_SAMPLE['T']},U={CPU_SAMPLE['U']},H={H},V={V} "
+                      f"fp32, torch {torch.__version__} linear+tanh + torchaudio rnnt_loss fwd+bwd "
+                      f"(oracle/ref_path.py = rnnt/joint.py:25-39 + rnnt/model.py:35-41), best of {max(1, steps)} after "
+                      f"{warmup} warm-up, {cells} cells, {dt:.2f} s/step on {cores} threads")
+    if one is not None:
+        out["one_thread"] = dict(value=cells / one, unit=UNIT, cores=1, s_per_step=one)
+    return out, dt
 
 
 def run_reference_arm(args):
@@ -154,7 +184,7 @@ def run_reference_arm(args):
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload=f"joint+loss fwd+bwd, bounded CPU sample {base['sample']}"),
+                config=dict(workload=f"joint+loss fwd+bwd on the host CPU, bounded sample: {base['sample']}"),
                 cpu_baseline=base,
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -230,34 +260,92 @@ def other_configs(torch, dev):
     out["cpu_reference_shape_B4_T200_U40_V1024"] = loss_cfg(4, 200, 40, 1024, False, 20)
     out["ragged_B32_T400_U100_V1024"] = loss_cfg(32, 400, 100, 1024, True, 5)
     out["stress_B8_T1500_U300_V4096_ragged"] = loss_cfg(8, 1500, 300, 4096, True, 2)
-    # batched greedy decode, B=64, T=400, ConvPredictor at default init, max_length 200
+    # batched greedy decode (BASELINE configs[4]): B=64, T=400, ConvPredictor at default init, max_length 200
+    import rnnt_b200.functional as RF
     torch.manual_seed(0)
+    E = 512
     joint = rnnt_b200.JointNetwork(-1, -1, H, V)
     with torch.no_grad():
-        joint.joint_ln.bias[V - 1] += 1.0
-    model = rnnt_b200.RNNTModel(rnnt_b200.ConvPredictor(V, H, 512, 0.3), torch.nn.Identity(), joint).to(dev).eval()
-    feats = torch.randn(64, 400, H, device=dev)
-    lens = torch.randint(200, 401, (64,)); lens[0] = 400
+        joint.joint_ln.bias[V - 1] += 1.8       # blank wins ~80 % of the steps: utterances both emit and advance
+    model = rnnt_b200.RNNTModel(rnnt_b200.ConvPredictor(V, H, E, 0.3), torch.nn.Identity(), joint).eval()
+    feats_cpu = torch.randn(64, 400, H)
+    lens = torch.randint(300, 401, (64,)); lens[0] = 400
+    # the reference's own loop (rnnt/model.py:90-128 restated in oracle/ref_path.py) on the host cores, 4 utterances
+    from oracle.ref_path import ref_greedy_decode
+    sd = {k: v.detach() for k, v in model.predictor.state_dict().items()}
+    n_ref = 4
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    ref_toks = [ref_greedy_decode(feats_cpu[i:i + 1, : int(lens[i])], joint.joint_ln.weight.detach(),
+                                  joint.joint_ln.bias.detach(), sd, V - 1, 200) for i in range(n_ref)]
+    cpu_s = time.perf_counter() - t0
+    cpu_frames = int(lens[:n_ref].sum())
+    model = model.to(dev)
+    feats = feats_cpu.to(dev)
     model.greedy_decode_features(feats, lens, max_length=200)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    toks = model.greedy_decode_features(feats, lens, max_length=200)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    out["greedy_decode_B64_T400"] = dict(ms_total=dt * 1e3, frames=int(lens.sum()), frames_per_s=int(lens.sum()) / dt,
-                                         tokens=sum(len(x) for x in toks),
-                                         note="whole loop in one persistent kernel, wall clock incl. result read-back")
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        toks = model.greedy_decode_features(feats, lens, max_length=200)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    cyc = RF._last_decode_phase_cycles.tolist()
+    frames, ntok = int(lens.sum()), sum(len(x) for x in toks)
+    steps = max(int(lens[b]) + len(toks[b]) for b in range(64))       # kernel iterations = longest utterance's decisions
+    w_bytes = 4 * (V * H + E * 3 * E + E * 5 * E + H * E)             # fp32 weights every step streams from L2
+    out["greedy_decode_B64_T400"] = dict(
+        ms_total=best * 1e3, frames=frames, frames_per_s=frames / best, tokens=ntok, steps=steps,
+        us_per_step=best * 1e6 / steps, weight_bytes_per_step=w_bytes, l2_gbs=w_bytes * steps / best / 1e9,
+        bound="latency: one cooperative kernel, grid barriers between the phases of a step; the fp32 weights (14.7 MB) "
+              "are L2-resident, so neither HBM nor the tensor pipe is the limit",
+        phase_cycles=dict(zip(["P1", "P2", "P3", "P4", "P5", "P6", "-", "grid_barriers"], cyc)),
+        tokens_match_cpu_reference=[toks[i] == ref_toks[i] for i in range(n_ref)],
+        cpu_reference=dict(frames_per_s=cpu_frames / cpu_s, s_total=cpu_s, utterances=n_ref, frames=cpu_frames,
+                           cores=os.cpu_count(), kind="port",
+                           note="rnnt/model.py:90-128 restated (oracle/ref_path.py), one utterance at a time"),
+        note="whole batched loop in one persistent kernel, wall clock incl. result read-back, best of 3")
     return out
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+KERNEL_FAMILIES = ["prep", "joint_gemm_fwd", "lattice", "joint_gemm_bwd", "dh_gemm", "dw_gemm", "db", "other"]
+GEMM_FAMILIES = ("joint_gemm_fwd", "joint_gemm_bwd", "dh_gemm", "dw_gemm")
+
+
+def kernel_table(fam_ms, fam_n, nsteps, ms_step, cells_rank, bwd_frac, peak_tflops, hbm_peak):
+    """Per kernel family: ms per step, share of the step, achieved TFLOP/s on the FLOPs it executed (the backward GEMMs
+    only run over half-tiles with non-zero gradients) and that as a fraction of `peak_tflops`."""
+    kern = {}
+    gemm_flops = cells_rank * FLOP_PER_CELL_GEMM
+    for i, nm in enumerate(KERNEL_FAMILIES):
+        if fam_n[i] == 0:
+            continue
+        per_step_ms = fam_ms[i] / nsteps
+        k = dict(ms_per_step=per_step_ms, launches_per_step=fam_n[i] / nsteps, share=per_step_ms / ms_step)
+        if nm in GEMM_FAMILIES:
+            frac = 1.0 if nm == "joint_gemm_fwd" else bwd_frac
+            k["flops_per_step"] = gemm_flops * frac
+            k["tflops"] = gemm_flops * frac / (per_step_ms * 1e-3) / 1e12
+            k["frac_of_peak"] = k["tflops"] / peak_tflops
+        if nm == "lattice":
+            # algorithmic bytes: each direction reads lp (8 B/cell) and writes alpha or beta (4 B/cell).  The kernel is
+            # bound by the (T+U)-step dependency chain of the wavefront (one CTA per utterance and direction), not by HBM.
+            k["gbs"] = cells_rank * 24 / (per_step_ms * 1e-3) / 1e9
+            k["hbm_frac"] = k["gbs"] / hbm_peak
+            k["ns_per_antidiagonal"] = per_step_ms * 1e6 / (T + U)
+            k["bound"] = "latency: T+U dependent anti-diagonal steps, 2*B CTAs"
+        kern[nm] = k
+    return kern
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from rnnt_b200 import _lib
     import rnnt_b200.functional as RF
     from rnnt_b200.functional import joint_rnnt_loss
-    from rnnt_b200.parallel import GradAllReducer
+    from rnnt_b200.parallel import WeightGradBucket
     os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,23 +359,36 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    n_sets = 3   # rotating input sets: 3 x 70 MB > 126 MB L2, so inputs are L2-cold every step
-    sets = [synth_inputs(torch, 1234 + rank * 16 + i, dev) for i in range(n_sets)]
-    for s in sets:
-        for k in ("enc", "pred", "W", "b"):
-            s[k].requires_grad_(True)
-    pred_grad_stub = torch.zeros(PRED_GRAD_ELEMS, dtype=torch.float32, device=dev)
-    reducer = GradAllReducer([], average=True)
+    # workload: N=1 -> configs[1] (B=32); N>1 -> configs[2] (global 256 sharded by utterance) unless --global-batch 0
+    strong = world > 1 and args.global_batch > 0
+    if strong and args.global_batch % world:
+        raise SystemExit(f"--global-batch {args.global_batch} must divide by the number of GPUs ({world})")
+    Bg = args.global_batch // world if strong else B
+    cells_rank = Bg * T * (U + 1)
 
-    def step(s):
+    def make_sets(b, n_sets=3):   # rotating input sets: >= 3 x 70 MB > 126 MB L2, so inputs are L2-cold every step
+        sets = [synth_inputs(torch, 1234 + rank * 16 + i, dev, b=b) for i in range(n_sets)]
+        for s_ in sets:
+            for k in ("enc", "pred", "W", "b"):
+                s_[k].requires_grad_(True)
+        return sets
+
+    sets = make_sets(Bg)
+    bucket = None
+    if world > 1:      # dW / db are written straight into the flat all-reduce bucket; predictor grads ride as a stub
+        bucket = WeightGradBucket(V, H, PRED_GRAD_ELEMS, dev, average=True)
+        bucket.time_collectives = True
+        RF.set_weight_grad_sink(bucket)
+
+    def step(s_, all_tiles=False):
         for k in ("enc", "pred", "W", "b"):
-            s[k].grad = None
-        loss = joint_rnnt_loss(s["enc"], s["pred"], s["W"], s["b"], s["targets"], s["T_len"], s["U_len"],
+            s_[k].grad = None
+        loss = joint_rnnt_loss(s_["enc"], s_["pred"], s_["W"], s_["b"], s_["targets"], s_["T_len"], s_["U_len"],
                                blank=-1, clamp=-1, reduction="mean", validate=False,
-                               skip_zero_tiles=not args.all_tiles)
-        loss.backward()
-        if world > 1:
-            reducer.all_reduce_grads([s["W"].grad, s["b"].grad, pred_grad_stub], wait=True)
+                               skip_zero_tiles=not (all_tiles or args.all_tiles))
+        loss.backward()          # with a bucket: the all-reduce of dW/db is already in flight under the dh GEMM
+        if bucket is not None:
+            bucket.finish()      # predictor stub slice + averaging; the compute stream waits for the result
         return loss
 
     def barrier():
@@ -295,45 +396,50 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_region(nsteps, use_sets, profile, sample_clocks, **kw):
+        sampler = ClockSampler(local_rank)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        if bucket is not None:
+            bucket.reset_timing()
+        if profile:
+            L.rnnt_b200_profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        last = None
+        for i in range(nsteps):
+            last = step(use_sets[i % len(use_sets)], **kw)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        fam_ms, fam_n = (C.c_float * 8)(), (C.c_int64 * 8)()
+        if profile:
+            _lib.check(L.rnnt_b200_profile_end(fam_ms, fam_n), "profile_end")
+        clocks = sampler.stop() if (sample_clocks and rank == 0) else None
+        nccl_ms = bucket.collective_ms() / nsteps if bucket is not None else 0.0
+        return dict(ms=ms, fam_ms=list(fam_ms), fam_n=list(fam_n), clocks=clocks, last=last, nccl_ms=nccl_ms)
+
     for i in range(args.warmup):
-        step(sets[i % n_sets])
+        step(sets[i % len(sets)])
     barrier()
 
-    # ---- timed region: K steps, CUDA events on the launch stream, clocks sampled, per-kernel events on
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    if not args.no_kernel_profile:
-        L.rnnt_b200_profile_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        last = step(sets[i % n_sets])
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    fam_ms = (C.c_float * 8)()
-    fam_n = (C.c_int64 * 8)()
-    _lib.check(L.rnnt_b200_profile_end(fam_ms, fam_n), "profile_end")
-    clocks = sampler.stop() if rank == 0 else None
-    loss_val = float(last.detach())
-    # secondary number: the same step with the backward forced over ALL half-tiles of the lattice (no zero-gradient skipping)
-    dense_ms = None
-    if not args.all_tiles:
-        args.all_tiles = True
+    # ---- headline timed region: K steps, CUDA events on the launch stream, clocks sampled, per-kernel events on
+    head = timed_region(args.steps, sets, not args.no_kernel_profile, True)
+    ms_total = head["ms"]
+    loss_val = float(head["last"].detach())
+
+    # ---- secondary numbers (single GPU only): every tile in the backward; a >= 3 s sustained loop under the power cap
+    dense_ms, sustained = None, None
+    if world == 1 and not args.all_tiles:
         for i in range(2):
-            step(sets[i % n_sets])
-        barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nd = max(2, args.steps // 2)
-        d0.record()
-        for i in range(nd):
-            step(sets[i % n_sets])
-        d1.record()
-        barrier()
-        dense_ms = d0.elapsed_time(d1) / nd
-        args.all_tiles = False
+            step(sets[i % len(sets)], all_tiles=True)
+        dense_ms = timed_region(max(2, args.steps // 2), sets, False, False, all_tiles=True)["ms"] / max(2, args.steps // 2)
+    if world == 1 and args.sustain_s > 0:
+        n_sus = max(args.steps, int(args.sustain_s * 1e3 / (ms_total / args.steps)) + 1)
+        sus = timed_region(n_sus, sets, not args.no_kernel_profile, True)
+        sustained = dict(steps=n_sus, ms_per_step=sus["ms"] / n_sus, seconds=sus["ms"] * 1e-3, clocks=sus["clocks"],
+                         fam_ms=sus["fam_ms"], fam_n=sus["fam_n"])
     RF.COLLECT_BACKWARD_STATS = True
     step(sets[0])
     torch.cuda.synchronize()
@@ -341,13 +447,25 @@ def run_gpu_arm(args):
     RF.COLLECT_BACKWARD_STATS = False
     bwd_frac = active_tiles / max(1, total_tiles)
 
+    # ---- round-1 workload for continuity (N>1 only): weak scaling, B=32 per GPU
+    weak_ms = None
+    if strong:
+        del sets
+        torch.cuda.empty_cache()
+        wsets = make_sets(B)
+        for i in range(3):
+            step(wsets[i % 3])
+        weak_ms = timed_region(max(5, args.steps // 2), wsets, False, False)["ms"] / max(5, args.steps // 2)
+        del wsets
+        torch.cuda.empty_cache()
+
     # ---- e2e: same step through the public API from pinned HOST buffers, result read back to host.
-    # Every step copies that step's inputs host->device (all 7 tensors, 69.9 MB) and reads its loss back; the copy of
+    # Every step copies that step's inputs host->device (all 7 tensors) and reads its loss back; the copy of
     # step i+1 runs on a side stream into the other device buffer while step i computes (double buffering).
-    host = synth_inputs(torch, 4321 + rank, dev, pin=True)
+    host = synth_inputs(torch, 4321 + rank, dev, b=Bg, pin=True)
     devbufs = []
     for _ in range(2):
-        d = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        d = {k: torch.empty_like(v, device=dev) for k, v in host.items()}      # keeps the (B,H,T)-view strides of enc
         for k in ("enc", "pred", "W", "b"):
             d[k].requires_grad_(True)
         devbufs.append(d)
@@ -390,40 +508,26 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks
-    times = torch.tensor([ms_total, e2e_s * 1e3, dense_ms or 0.0], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_s * 1e3, dense_ms or 0.0, weak_ms or 0.0, head["nccl_ms"]], dtype=torch.float64,
+                         device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, dense_ms = float(times[0]), float(times[1]), float(times[2])
+    ms_total, e2e_ms, dense_ms, weak_ms, nccl_ms = (float(x) for x in times)
 
     if rank == 0:
         peaks = load_peaks()
-        cells_step = B * T * (U + 1) * world
+        cells_step = cells_rank * world
         ms_step = ms_total / args.steps
         value = cells_step / (ms_step * 1e-3)
-        names = ["prep", "joint_gemm_fwd", "lattice", "joint_gemm_bwd", "dh_gemm", "dw_gemm", "db", "other"]
-        kern = {}
-        gemm_flops_per_step_rank = B * T * (U + 1) * FLOP_PER_CELL_GEMM
-        for i, nm in enumerate(names):
-            if fam_n[i] == 0:
-                continue
-            per_step_ms = fam_ms[i] / args.steps
-            kern[nm] = dict(ms_per_step=per_step_ms, launches_per_step=fam_n[i] / args.steps,
-                            share=per_step_ms / ms_step)
-            if nm in ("joint_gemm_fwd", "joint_gemm_bwd", "dh_gemm", "dw_gemm"):
-                # executed algorithmic FLOPs: the backward GEMMs only run over half-tiles with non-zero gradients
-                frac = 1.0 if nm == "joint_gemm_fwd" else bwd_frac
-                kern[nm]["flops_per_step"] = gemm_flops_per_step_rank * frac
-                kern[nm]["tflops"] = gemm_flops_per_step_rank * frac / (per_step_ms * 1e-3) / 1e12
-            if nm == "lattice":
-                # algorithmic bytes: each direction reads lp (8 B/cell) and writes alpha or beta (4 B/cell)
-                lat_bytes = B * T * (U + 1) * 24
-                kern[nm]["gbs"] = lat_bytes / (per_step_ms * 1e-3) / 1e9
-                kern[nm]["hbm_frac"] = kern[nm]["gbs"] / peaks["hbm"]
-                kern[nm]["ns_per_antidiagonal"] = per_step_ms * 1e6 / (T + U)
+        # regime of the headline timed region: a short burst runs at boost clocks, seconds-long loops at the power cap
+        regime = "sustained" if ms_total >= 2000.0 else "burst"
+        head_peak = peaks[regime]
+        kern = kernel_table(head["fam_ms"], head["fam_n"], args.steps, ms_step, cells_rank, bwd_frac, head_peak,
+                            peaks["hbm"])
         gemms = {k: v for k, v in kern.items() if "tflops" in v}
         if not gemms:   # --no-kernel-profile: no per-kernel events were recorded
             gemms = {"whole_step": dict(ms_per_step=ms_step, launches_per_step=1.0,
-                                        tflops=3 * gemm_flops_per_step_rank / (ms_step * 1e-3) / 1e12)}
+                                        tflops=(1 + 3 * bwd_frac) * cells_rank * FLOP_PER_CELL_GEMM / (ms_step * 1e-3) / 1e12)}
         dom = max(gemms, key=lambda k: gemms[k]["ms_per_step"])
         launches_dom = gemms[dom]["launches_per_step"]
         achieved = gemms[dom]["tflops"]
@@ -434,47 +538,88 @@ def run_gpu_arm(args):
         if tpath:     # DRAM bytes per launch of that kernel from the latest committed ncu --set full capture
             with open(tpath) as f:
                 traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
-        roofline = dict(bound="tensor", kernel=dom, achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s",
-                        frac=achieved / peaks["tflops"], traffic=traffic, peak_source=peaks["source"],
-                        flops_per_launch=gemms[dom].get("flops_per_step", gemm_flops_per_step_rank) / launches_dom,
-                        avg_launch_ms=gemms[dom]["ms_per_step"] / launches_dom,
-                        whole_step_frac_credited=(value / world) * 3 * FLOP_PER_CELL_GEMM / (peaks["tflops"] * 1e12),
-                        kernels=kern)
-        cpu_base, _ = time_cpu_reference(1, 1) if world == 1 and not args.no_cpu_baseline else (None, None)
+        exec_flops_rank = (1 + 3 * bwd_frac) * cells_rank * FLOP_PER_CELL_GEMM     # F over all tiles; G, dh, dW over active ones
+        per_gpu_cells_s = value / world
+        roofline = dict(
+            bound="tensor", kernel=dom, achieved=achieved, peak=head_peak, unit="TFLOP/s", frac=achieved / head_peak,
+            regime=f"{regime}: the headline timed region lasted {ms_total * 1e-3:.2f} s, so the denominator is the "
+                   f"{'burst (best-of-10)' if regime == 'burst' else 'sustained (4 s loop)'} cuBLAS bf16 figure",
+            traffic=traffic, peak_source=peaks["source"],
+            flops_per_launch=gemms[dom].get("flops_per_step", cells_rank * FLOP_PER_CELL_GEMM) / launches_dom,
+            avg_launch_ms=gemms[dom]["ms_per_step"] / launches_dom,
+            whole_step_frac_executed=exec_flops_rank / (ms_step * 1e-3) / 1e12 / head_peak,
+            whole_step_frac_crediting_skipped_tiles=per_gpu_cells_s * 3 * FLOP_PER_CELL_GEMM / (head_peak * 1e12),
+            note="whole_step_frac_executed counts the FLOPs the GEMM kernels really ran (2HV per cell in the forward, "
+                 "6HV per cell of an ACTIVE half-tile in the backward incl. the logit recompute); "
+                 "..._crediting_skipped_tiles credits the algorithmic 6HV on every cell, also those the backward "
+                 "skipped, so it is a throughput figure, not a utilisation",
+            kernels=kern)
+        if sustained is not None:
+            sk = kernel_table(sustained["fam_ms"], sustained["fam_n"], sustained["steps"], sustained["ms_per_step"],
+                              cells_rank, bwd_frac, peaks["sustained"], peaks["hbm"])
+            sg = {k: v for k, v in sk.items() if "tflops" in v}
+            roofline["sustained"] = dict(
+                seconds=sustained["seconds"], steps=sustained["steps"], ms_per_step=sustained["ms_per_step"],
+                value=cells_rank / (sustained["ms_per_step"] * 1e-3), unit=UNIT, peak=peaks["sustained"],
+                kernel=dom, achieved=sg[dom]["tflops"] if dom in sg else None,
+                frac=sg[dom]["tflops"] / peaks["sustained"] if dom in sg else None,
+                whole_step_frac_executed=exec_flops_rank / (sustained["ms_per_step"] * 1e-3) / 1e12 / peaks["sustained"],
+                clocks=sustained["clocks"], kernels=sk)
+        cpu_base, _ = time_cpu_reference(3, 1) if world == 1 and not args.no_cpu_baseline else (None, None)
         extra = None
         if world == 1 and not args.no_extra:
             try:
                 extra = other_configs(torch, dev)
             except Exception as exc:      # the headline line must not depend on the side runs
                 extra = dict(error=repr(exc))
+        if strong:
+            workload = (f"BASELINE configs[2]: global batch {args.global_batch} sharded by utterance, "
+                        f"{Bg} per GPU in one launch (T={T},U={U},H={H},V={V}), joint+loss fused fwd+bwd")
+        else:
+            workload = (f"BASELINE configs[1]: joint+loss fused fwd+bwd, per-GPU B={B},T={T},U={U},H={H},V={V}; "
+                        f"global batch {B * world}")
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp16",
-                    data="synthetic",
-                    config=dict(workload=f"joint+loss fused fwd+bwd, per-GPU B={B},T={T},U={U},H={H},V={V} "
-                                         f"(BASELINE configs[1]); global batch {B * world}",
-                                parallelism=f"dp{world} by utterance, all-reduce of {V * H + V + PRED_GRAD_ELEMS} "
-                                            "fp32 grads" if world > 1 else "single GPU",
-                                l2="3 rotating input sets (210 MB > 126 MB L2); every step also streams the 2.7 GB "
-                                   "activation residual and the gradient ring through HBM",
+                    ms_per_step=ms_step, higher_is_better=True, scaling="strong" if strong else "weak",
+                    vs_baseline=None, dtype="fp16", data="synthetic",
+                    config=dict(workload=workload, global_batch=Bg * world, per_gpu_batch=Bg,
+                                parallelism=(f"dp{world} by utterance; dW/db written into one flat bucket, NCCL "
+                                             f"all-reduce of {V * H + V} joint + {PRED_GRAD_ELEMS} predictor(stub) fp32 "
+                                             "grads, the joint part overlapped with the dh GEMM") if world > 1 else "single GPU",
+                                encoder_layout="(B,T,H) view of a (B,H,T) tensor (rnnt/model.py:28), read in place",
+                                l2=f"3 rotating input sets ({3 * 70 * Bg // 32} MB > 126 MB L2); every step also streams the "
+                                   "fp16 activation residual and the gradient ring through HBM",
                                 operands="fp16 x fp16 -> fp32 (TMEM), fp32 elsewhere",
                                 backward_tiles=dict(active=active_tiles, total=total_tiles, fraction=bwd_frac,
                                                     note="half-tiles (16 t x 4 u lattice blocks) whose fp16 logit-"
                                                          "gradients are all zero (occupancy < 2^-25) are skipped; "
                                                          "--all-tiles disables"),
                                 loss=loss_val),
-                    clocks=clocks,
+                    clocks=head["clocks"],
                     e2e=dict(value=cells_step / (e2e_ms * 1e-3 / args.steps), unit=UNIT,
                              h2d_bytes_per_step=h2d, d2h_bytes_per_step=4, ms_per_step=e2e_ms / args.steps),
-                    gpu_launches=int(sum(fam_n)),
+                    gpu_launches=int(sum(head["fam_n"])),
                     all_tiles=(dict(ms_per_step=dense_ms, value=cells_step / (dense_ms * 1e-3), unit=UNIT,
-                                    note="same step, backward over every half-tile of the lattice (zero-gradient ones not skipped)")
+                                    frac_credited=cells_rank * 3 * FLOP_PER_CELL_GEMM / (dense_ms * 1e-3) / 1e12 / head_peak,
+                                    frac_executed=cells_rank * 4 * FLOP_PER_CELL_GEMM / (dense_ms * 1e-3) / 1e12 / head_peak,
+                                    note="same step, backward over every half-tile of the lattice (zero-gradient ones "
+                                         "not skipped): the data-independent number; credited = 6HV per cell, executed "
+                                         "= 8HV per cell (the backward recomputes the logits)")
                                if dense_ms else None),
                     roofline=roofline)
+        if world > 1:
+            line["nccl"] = dict(ms_per_step=nccl_ms, bytes_per_step=4 * (V * H + V + PRED_GRAD_ELEMS),
+                                note="device time of the step's NCCL all-reduces (events on the side stream, max over "
+                                     "ranks); the joint bucket's share runs under the dh GEMM")
+        if weak_ms:
+            line["weak_b32_per_gpu"] = dict(ms_per_step=weak_ms, value=B * T * (U + 1) * world / (weak_ms * 1e-3),
+                                            unit=UNIT, global_batch=B * world,
+                                            note="round-1 workload for continuity: B=32 per GPU, weak scaling")
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if extra is not None:
             line["other_configs"] = extra
         print(json.dumps(line), flush=True)
+    RF.set_weight_grad_sink(None)
     if world > 1:
         dist.destroy_process_group()
 
@@ -488,6 +633,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true", help="skip the per-kernel CUDA events")
     ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE.json configs")
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH,
+                    help="N>1: global batch sharded over the GPUs (BASELINE configs[2]); 0 = weak scaling, B=32 per GPU")
+    ap.add_argument("--sustain-s", type=float, default=3.0,
+                    help="N=1: length of the extra sustained (power-capped) loop in seconds; 0 disables")
     ap.add_argument("--all-tiles", action="store_true",
                     help="backward processes every half-tile of the lattice (also those whose fp16 gradients are all zero)")
     args = ap.parse_args()

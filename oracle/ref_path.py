@@ -35,3 +35,36 @@ def ref_loss_and_grads(enc, pred, W, b, targets, T_len, U_len, reduction="none",
     else:
         out.backward(torch.ones_like(out) if dcost is None else dcost)
     return out.detach(), enc.grad, pred.grad, W.grad, b.grad
+
+
+def ref_conv_predictor(ids, sd):
+    """rnnt/predictor.py:209-229 (eval mode) with torch functional ops on a state_dict.  ids (1,L) int64 -> (1,L,D)."""
+    F = torch.nn.functional
+    x = F.embedding(ids, sd["embedding.weight"])
+    x = F.layer_norm(x, x.shape[-1:], sd["input_layer_norm.weight"], sd["input_layer_norm.bias"])
+    x = x.permute(0, 2, 1)
+    for name in ("conv1", "conv2"):                                   # rnnt/causalconv.py:23-30: left zero padding k-1
+        w = sd[name + ".conv.weight"]
+        x = F.gelu(F.conv1d(F.pad(x, (w.shape[2] - 1, 0)), w, sd[name + ".conv.bias"]))
+    x = F.linear(x.permute(0, 2, 1), sd["linear.weight"], sd["linear.bias"])
+    return F.layer_norm(x, x.shape[-1:], sd["output_layer_norm.weight"], sd["output_layer_norm.bias"])
+
+
+@torch.no_grad()
+def ref_greedy_decode(audio_features, W, b, pred_sd, blank, max_length=200, max_outputs_per_step=10):
+    """rnnt/model.py:90-128 (_greedy_decode_conv) for ONE utterance on given encoder features (1,T,H): joint
+    single_forward (joint.py:44-55) + argmax + `.item()` per step, full-history predictor re-run per emitted token."""
+    tokens = [blank]
+    t, per, T = 0, 0, audio_features.shape[1]
+    feats = ref_conv_predictor(torch.tensor([tokens], dtype=torch.int64), pred_sd)
+    while t < T and len(tokens) < max_length:
+        logits = torch.nn.functional.linear(torch.tanh(audio_features[:, t, :] + feats[:, -1, :]), W, b)
+        tok = logits.argmax(dim=-1).item()
+        if tok == blank or per >= max_outputs_per_step:
+            t += 1
+            per = 0
+        else:
+            tokens.append(tok)
+            feats = ref_conv_predictor(torch.tensor([tokens], dtype=torch.int64), pred_sd)
+            per += 1
+    return tokens[1:]

@@ -253,11 +253,21 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// Deterministic mode of the backward: sums that cross CTAs are accumulated as 64-bit fixed point (2^-36 units; integer
-// addition is associative, so the result does not depend on the order in which the atomics land).  The operands are the
-// S-scaled gradients (|x| < 2^20 by construction), so 2^-36 resolution is ~1e-9 relative to typical entries.
-constexpr float kFxScale = 68719476736.f;             // 2^36
-constexpr double kFxInv = 1.0 / 68719476736.0;
+// Gradient scale.  The logit-gradients g (|g| <= |dcost_b|: softmax x occupancy minus occupancy-weighted one-hots) are
+// stored in fp16 as g * S with S = 2^kGradShift / 2^ceil(log2 max_b |dcost_b|), i.e. max |g S| in [2^11, 2^12]: typical
+// entries (occupancy ~1e-2 x softmax ~1e-3 = 1e-5 of the maximum) then sit well inside fp16's NORMAL range (>= 6.1e-5)
+// instead of its subnormals, which is what bounded the gradient error at the full bench shape (1.1e-3 -> 3e-4 relative).
+constexpr int kGradShift = 12;
+// Occupancy sparsity threshold, in units of max_b |dcost_b|: half-tiles whose every logit-gradient is below 2^-25 of the
+// largest possible gradient entry are dropped from the backward (the fp32 reference itself resolves 2^-24 of it).
+constexpr float kSkipBelow = 2.98023224e-8f * static_cast<float>(1 << kGradShift);   // 2^-25 in S-scaled units
+
+// Deterministic mode of the backward: sums that cross CTAs are accumulated as 64-bit fixed point (2^-26 units; integer
+// addition is associative, so the result does not depend on the order in which the atomics land).  The operands are
+// the S-scaled gradients: entries are bounded by 2^13 max|W| U1 (d_enc), 2^13 B (T+U) (dW) < 2^36, typical ones are O(1),
+// so 2^-26 resolution is ~1e-8 relative and the 64-bit sums cannot overflow.
+constexpr float kFxScale = 67108864.f;                // 2^26
+constexpr double kFxInv = 1.0 / 67108864.0;
 __device__ __forceinline__ void fx_add(long long* p, float x) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(x * kFxScale)));
 }

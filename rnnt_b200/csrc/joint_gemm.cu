@@ -51,7 +51,10 @@ struct SmemLayout {
   static constexpr int ring = 0;
   static constexpr int xchg = ring + kStages * kStageBytes;   // F: set-1 -> set-0 softmax partials (2 x 128 x 16 B)
   static constexpr int bars = xchg + 2 * kTileM * 16;
-  static constexpr int total = bars + 256;
+  // producers, T-contiguous encoder layout: per half-tile a double-buffered 16(t) x 64(k) fp32 transposing stage
+  static constexpr int enc_stage = bars + 256;
+  static constexpr int total_noprod = enc_stage;
+  static constexpr int total = enc_stage + 2 * 2 * kTileT * kBK * 4;
 };
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -75,7 +78,9 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int idx) {
 size_t joint_gemm_smem_bytes() { return SmemLayout::total + 1024; }
 int joint_gemm_scratch_tiles(int grid) { return grid * kScratchSlots; }
 
-template <int MODE, bool PRODUCE>  // MODE 0 = forward (lse + gather), 1 = backward (gradient ring)
+// MODE 0 = forward (lse + gather), 1 = backward (gradient ring); PRODUCE: activation producer warps present;
+// TMAJOR: the producers read T-contiguous encoder features (the (B,T,H) view of a (B,H,T) tensor) instead of H-contiguous
+template <int MODE, bool PRODUCE, bool TMAJOR = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PRODUCE ? kThreadsProd : kThreadsNoProd, 1)
 joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
                   const __grid_constant__ CUtensorMap tmH2, JointArgs p) {
@@ -346,14 +351,25 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     // the 16-byte column chunk c = l & 7 (8 hidden units) of the four rows (t-row 2(rs>>1) + i) x (u = 2(rs&1) + j),
     // rs = l >> 3: (2 + 2) x 8 inputs -> 32 tanh -> four 16-byte global stores; the 8 lanes of one row write 128
     // contiguous bytes.
+    //
+    // Encoder layout.  H-contiguous features (enc_sh == 1) are read straight into that register tile (two float4 per
+    // frame).  The reference hands the joint the (B,T,H) VIEW of the encoder's (B,H,T) output (rnnt/model.py:27-28),
+    // i.e. T-contiguous memory (enc_st == 1): the 4 warps of a half-tile then fetch its 64(k) x 16(t) fp32 box with
+    // fully used 64-byte row segments (lane = (k row, 4 frames): two float4 loads per chunk), transpose it through a
+    // double-buffered, XOR-swizzled shared-memory stage (conflict-free both ways) and read their register tile from
+    // there -- no transposed copy of the features in HBM, same number of L1 wavefronts as the H-contiguous path.
     const int rg = warp - kFirstProdWarp;
     const int c = lane & 7, rs = lane >> 3;
     const int sub = rg >> 2, tq = (rg & 3) * 4 + (rs >> 1) * 2, uq = (rs & 1) * 2;
-    uint32_t cnt = 0;
+    constexpr bool t_major = TMAJOR;
+    const bool vec_ok = ((p.enc_sh | p.enc_sb) & 3) == 0;     // 16-byte aligned rows of the (B,H,T) tensor
+    const int wl = rg & 3, kk = lane >> 2, tq4 = lane & 3;    // T-major fetch: k rows 16 wl + kk (+8), frames 4 tq4 .. +3
+    float* stage = reinterpret_cast<float*>(smem_gen + SL::enc_stage) + sub * (2 * kTileT * kBK);
+    uint32_t cnt = 0, cc = 0;                                 // cc: running chunk counter = stage buffer parity
     RB_TILE_LOOP(cnt) {
       const int q = base_ + rank;
       const int hid = half_id(q, sub);
-      if (hid < 0) {            // nothing to produce for this half: keep the barrier protocol
+      if (hid < 0) {            // nothing to produce for this half (uniform over its 4 warps): keep the barrier protocol
         if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
         __syncwarp();
         if (lane == 0) mbar_arrive(h_ready + 8 * (cnt & 1));
@@ -361,70 +377,82 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       }
       const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, p.T, p.U1, hid);
       const int row0 = h_row0(q, sub, hid, cnt);
-      // Encoder features arrive either H-contiguous (enc_sh == 1) or, as rnnt/model.py:28 hands them over, as the
-      // (B,T,H) view of the encoder's (B,H,T) output (enc_st == 1, T-contiguous): then the lane's two frames are the
-      // two halves of one 8-byte load per hidden unit, straight from the encoder's buffer (no transpose copy).
-      const bool t_major = p.enc_sh != 1;
-      const int te0 = tc.t0 + tq;                                   // first of this lane's two frames
-      const bool pair_ok = t_major && (te0 + 1 < p.T) && ((p.enc_sh | p.enc_sb) & 1) == 0;
       const float* e_ptr[2];
       const float* p_ptr[2];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(te0 + i, p.T - 1)) * p.enc_st +
-                   static_cast<long long>(8 * c) * p.enc_sh;
+        e_ptr[i] = p.enc + tc.b * p.enc_sb + static_cast<long long>(min(tc.t0 + tq + i, p.T - 1)) * p.enc_st + 8 * c;
         p_ptr[i] = p.pred + tc.b * p.pred_sb + static_cast<long long>(min(tc.u0 + uq + i, p.U1 - 1)) * p.pred_su + 8 * c;
       }
-      float4 e_cur[2][2], p_cur[2][2];
-      auto load_chunk = [&](int kc, float4 (&e)[2][2], float4 (&pp)[2][2]) {
-        const int col = kc * kBK + 8 * c;
-        if (col < p.H) {
-          if (!t_major) {
+      float4 e_cur[2][2], p_cur[2][2], g_cur[2];
+      auto load_enc = [&](int kc, float4 (&e)[2][2]) {         // H-contiguous: straight into the register tile
+        const bool ok = kc * kBK + 8 * c < p.H;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              e[i][0] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK));
-              e[i][1] = __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK) + 1);
-            }
-          } else {
-            float ev[2][8];
-            const long long koff = static_cast<long long>(kc) * kBK * p.enc_sh;
-            if (pair_ok) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 v = __ldg(reinterpret_cast<const float2*>(e_ptr[0] + koff + j * p.enc_sh));
-                ev[0][j] = v.x; ev[1][j] = v.y;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                ev[0][j] = __ldg(e_ptr[0] + koff + j * p.enc_sh);
-                ev[1][j] = __ldg(e_ptr[1] + koff + j * p.enc_sh);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              e[i][0] = make_float4(ev[i][0], ev[i][1], ev[i][2], ev[i][3]);
-              e[i][1] = make_float4(ev[i][4], ev[i][5], ev[i][6], ev[i][7]);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            pp[i][0] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK));
-            pp[i][1] = __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK) + 1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) e[i][0] = e[i][1] = pp[i][0] = pp[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 2; ++i) {
+          e[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          e[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(e_ptr[i] + kc * kBK) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      load_chunk(0, e_cur, p_cur);
+      auto load_pred = [&](int kc, float4 (&pp)[2][2]) {
+        const bool ok = kc * kBK + 8 * c < p.H;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          pp[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pp[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(p_ptr[i] + kc * kBK) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto fetch_t = [&](int kc, float4 (&g)[2]) {             // T-contiguous: this lane's 2 (k rows) x 4 frames
+        const int t = tc.t0 + 4 * tq4;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = kc * kBK + 16 * wl + kk + 8 * h;
+          g[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < p.H) {
+            const float* src = p.enc + tc.b * p.enc_sb + static_cast<long long>(k) * p.enc_sh;
+            if (vec_ok && t + 3 < p.T) {
+              g[h] = __ldg(reinterpret_cast<const float4*>(src + t));
+            } else {
+              g[h].x = __ldg(src + min(t, p.T - 1));
+              g[h].y = __ldg(src + min(t + 1, p.T - 1));
+              g[h].z = __ldg(src + min(t + 2, p.T - 1));
+              g[h].w = __ldg(src + min(t + 3, p.T - 1));
+            }
+          }
+        }
+      };
+      // stage[buf][t][k ^ ((t >> 2 & 3) << 3)]: writers (fixed frame offset, lanes = 8 k x 4 frame groups) and readers
+      // (fixed frame, 8 lanes x 8 consecutive k) both touch all 32 banks exactly once
+      auto stage_put = [&](uint32_t buf, const float4 (&g)[2]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float* dst = stage + buf * (kTileT * kBK) + (4 * tq4) * kBK + ((16 * wl + kk + 8 * h) ^ (tq4 << 3));
+          dst[0] = g[h].x; dst[kBK] = g[h].y; dst[2 * kBK] = g[h].z; dst[3 * kBK] = g[h].w;
+        }
+      };
+      auto stage_get = [&](uint32_t buf, float4 (&e)[2][2]) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float4* src = reinterpret_cast<const float4*>(stage + buf * (kTileT * kBK) + (tq + i) * kBK +
+                                                              ((8 * c) ^ (wl << 3)));
+          e[i][0] = src[0];
+          e[i][1] = src[1];
+        }
+      };
+      if (t_major) fetch_t(0, g_cur); else load_enc(0, e_cur);
+      load_pred(0, p_cur);
       // stay at most two units ahead of the tensor pipe: unit cnt-2 must be fully consumed (also keeps the
       // two-phase h_ready / tile_done barriers and the 4-slot scratch unambiguous)
       if (cnt >= 2) mbar_wait(tile_done + 8 * (cnt & 1), ((cnt >> 1) - 1) & 1);
       // row of (t-row tq + i, u = uq + j) inside the half-tile: (tq + i) * 4 + uq + j
       __half* out_base = p.h_out + static_cast<long long>(row0 + tq * 4 + uq) * p.Hp + 8 * c;
-      for (int kc = 0; kc < nk; ++kc) {
+      for (int kc = 0; kc < nk; ++kc, ++cc) {
         if (p.dbg & 2) break;   // diagnostics: leave the buffer's previous contents (valid data from an earlier call)
+        if (t_major) {
+          stage_put(cc & 1, g_cur);
+          if (kc + 1 < nk) fetch_t(kc + 1, g_cur);             // next box in flight while this one is consumed
+          named_bar_sync(4 + sub, 128);                        // the half-tile's 4 warps: box complete, buffer cc-1 free
+          stage_get(cc & 1, e_cur);
+        }
         uint4 w[2][2];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {        // t-row
@@ -438,7 +466,10 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           }
         }
         // the inputs of the next chunk are requested before the stores of this one are issued
-        if (kc + 1 < nk) load_chunk(kc + 1, e_cur, p_cur);
+        if (kc + 1 < nk) {
+          if (!t_major) load_enc(kc + 1, e_cur);
+          load_pred(kc + 1, p_cur);
+        }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -464,23 +495,24 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 int launch_joint_gemm(int mode, bool produce, const CUtensorMap& tmW, const CUtensorMap& tmH, const CUtensorMap& tmH2,
                       const JointArgs& args, long long max_slots, cudaStream_t stream) {
   ProfScope prof_(mode == 0 ? kProfJointF : kProfJointG, stream);
-  const size_t smem = SmemLayout::total + 1024;
+  const size_t smem = (produce ? SmemLayout::total : SmemLayout::total_noprod) + 1024;
   const long long want_pairs = std::max<long long>(1, (max_slots + 3) / 4);   // 2 slots per CTA, 2 CTAs per pair
-#define RB_LAUNCH_JG(M, P)                                                                                         \
+#define RB_LAUNCH_JG(M, P, TM)                                                                                     \
   do {                                                                                                             \
-    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(joint_gemm_kernel<M, P, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                        (int)smem));                                                                \
-    const int grid = 2 * static_cast<int>(std::min<long long>(max_cta_pairs(reinterpret_cast<const void*>(joint_gemm_kernel<M, P>), P ? kThreadsProd : kThreadsNoProd, smem), want_pairs));                 \
-    if (args.dbg & 8) fprintf(stderr, "rnnt_b200: joint gemm mode %d produce %d grid %d\n", M, (int)P, grid);       \
-    joint_gemm_kernel<M, P><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, tmH2, args);            \
+    const int grid = 2 * static_cast<int>(std::min<long long>(max_cta_pairs(reinterpret_cast<const void*>(joint_gemm_kernel<M, P, TM>), P ? kThreadsProd : kThreadsNoProd, smem), want_pairs));                 \
+    if (args.dbg & 8) fprintf(stderr, "rnnt_b200: joint gemm mode %d produce %d t-major %d grid %d\n", M, (int)P, (int)TM, grid); \
+    joint_gemm_kernel<M, P, TM><<<grid, P ? kThreadsProd : kThreadsNoProd, smem, stream>>>(tmW, tmH, tmH2, args);            \
   } while (0)
+  const bool t_major = args.enc_sh != 1;
   if (mode == 0) {
     RB_REQUIRE(produce, -30, "forward joint kernel always produces the activations");
-    RB_LAUNCH_JG(0, true);
+    if (t_major) RB_LAUNCH_JG(0, true, true); else RB_LAUNCH_JG(0, true, false);
   } else if (produce) {
-    RB_LAUNCH_JG(1, true);
+    if (t_major) RB_LAUNCH_JG(1, true, true); else RB_LAUNCH_JG(1, true, false);
   } else {
-    RB_LAUNCH_JG(1, false);
+    RB_LAUNCH_JG(1, false, false);
   }
 #undef RB_LAUNCH_JG
   RB_CUDA_CHECK(cudaGetLastError());

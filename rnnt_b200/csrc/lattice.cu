@@ -15,8 +15,8 @@
 namespace rb {
 namespace {
 
-// Also derives the exact power-of-two scale S that maps max_b |dcost_b| into (0.5, 1]: the backward stores
-// logit-gradients in fp16 as g*S (full use of fp16's range whatever the loss scaling) and its epilogues apply 1/S.
+// Also derives the exact power-of-two scale S that maps max_b |dcost_b| into [2^(kGradShift-1), 2^kGradShift): the backward
+// stores logit-gradients in fp16 as g*S (full use of fp16's range whatever the loss scaling) and its epilogues apply 1/S.
 __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __restrict__ U_len, int B, int T, int U1,
                                   int* __restrict__ tile_off, int* __restrict__ err_flag,
                                   const float* __restrict__ dcost, float* __restrict__ gscale) {
@@ -30,11 +30,11 @@ __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __re
     } else {
       mx = 1.f;
     }
-    float S = 1.f;
+    float S = static_cast<float>(1 << kGradShift);
     if (mx > 0.f && mx < INFINITY) {
       int e;
       frexpf(mx, &e);          // mx = m * 2^e, m in [0.5, 1)
-      S = ldexpf(1.f, -e);     // mx * S in [0.5, 1)
+      S = ldexpf(1.f, kGradShift - e);     // mx * S in [2^(kGradShift-1), 2^kGradShift)
     }
     gscale[0] = S;
     gscale[1] = 1.f / S;
@@ -202,10 +202,11 @@ __global__ void coef_kernel(const float* __restrict__ lp, const float* __restric
 }
 
 // ---- occupancy sparsity of the backward.  The logit-gradients of a cell are bounded by max(|gamma'|,|eB'|,|eE'|)
-// (coef already carries dcost * S); below 2^-25 every fp16 value stored in the gradient ring would round to zero, so
-// a HALF-TILE (16 t x 4 u = 64 cells) whose cells are all below that bound contributes exactly nothing to
-// dh / dW / db and is dropped from the backward's work list.  One warp per half-tile, then a single-block compaction
-// (order preserved).  In dense mode every half-tile that holds at least one valid cell stays.
+// (coef already carries dcost * S).  A HALF-TILE (16 t x 4 u = 64 cells) whose cells are all below 2^-25 of the largest
+// possible gradient entry max_b |dcost_b| (kSkipBelow; half the resolution fp32 has for that entry) is dropped from the
+// backward's work list: what it would add to dh / dW / db is below the rounding of the terms that dominate them.
+// One warp per half-tile, then a single-block compaction (order preserved).  In dense mode (RNNT_B200_ALL_TILES) every
+// half-tile that holds at least one valid cell stays.
 __global__ void tile_activity_kernel(const float4* __restrict__ coef, const int* __restrict__ T_len,
                                      const int* __restrict__ U_len, const int* __restrict__ tile_off, int B, int T,
                                      int U1, int dense, unsigned char* __restrict__ flags) {
@@ -233,7 +234,7 @@ __global__ void tile_activity_kernel(const float4* __restrict__ coef, const int*
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       any_valid |= __shfl_xor_sync(0xffffffffu, any_valid, o);
     }
-    if (lane == 0) flags[hid] = (any_valid && (dense || mx > 2.98023224e-8f)) ? 1 : 0;   // 2^-25
+    if (lane == 0) flags[hid] = (any_valid && (dense || mx > kSkipBelow)) ? 1 : 0;
   }
 }
 

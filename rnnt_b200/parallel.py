@@ -54,7 +54,8 @@ class WeightGradBucket:
             self.event = torch.cuda.Event()
             self.event.record(torch.cuda.current_stream(self.device))   # materialises the cudaEvent_t handle
         self.pending = False
-        self.seconds_in_flight = 0.0
+        self.time_collectives = False      # bench.py: bracket every collective with CUDA events on the side stream
+        self._timing = []
 
     @property
     def joint_slice(self):
@@ -66,6 +67,25 @@ class WeightGradBucket:
 
     def _world(self):
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def _all_reduce(self, t):
+        if self.time_collectives and self.stream is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.device))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            e1.record(torch.cuda.current_stream(self.device))
+            self._timing.append((e0, e1))
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def reset_timing(self):
+        self._timing = []
+
+    def collective_ms(self) -> float:
+        """Summed device time of the all-reduces since reset_timing() (synchronises)."""
+        if self.stream is not None:
+            self.stream.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self._timing))
 
     # ---- sink protocol used by rnnt_b200.functional._FusedJointLoss.backward
     def accepts(self, V, H, device) -> bool:
@@ -83,9 +103,9 @@ class WeightGradBucket:
         if self.stream is not None:
             self.stream.wait_event(self.event)
             with torch.cuda.stream(self.stream):
-                dist.all_reduce(self.joint_slice, op=dist.ReduceOp.SUM, group=self.group)
+                self._all_reduce(self.joint_slice)
         else:
-            dist.all_reduce(self.joint_slice, op=dist.ReduceOp.SUM, group=self.group)
+            self._all_reduce(self.joint_slice)
         self.pending = True
 
     def finish(self):
@@ -104,7 +124,7 @@ class WeightGradBucket:
         with ctx:
             rest = self.extra_slice if self.pending else self.flat
             if rest.numel():
-                dist.all_reduce(rest, op=dist.ReduceOp.SUM, group=self.group)
+                self._all_reduce(rest)
             if self.average:
                 self.flat.div_(world)
         if self.stream is not None:

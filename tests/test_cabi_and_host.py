@@ -151,7 +151,7 @@ def test_ring_chunking_and_sharding_helpers():
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from rnnt_b200.parallel import GradAllReducer, shard_bounds
+from rnnt_b200.parallel import GradAllReducer, WeightGradBucket, shard_bounds
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 lo, hi = shard_bounds(8, world, rank)
@@ -164,6 +164,19 @@ red_sum = GradAllReducer([], average=False)
 g3 = torch.ones(7) * (rank + 1)
 red_sum.all_reduce_grads([g3])
 assert torch.allclose(g3, torch.full((7,), 3.0))
+# flat bucket of the overlapped path: the sink protocol the fused backward drives, on CPU tensors
+bk = WeightGradBucket(6, 4, 5, "cpu", average=True)
+assert bk.accepts(6, 4, "cpu") and not bk.accepts(6, 8, "cpu")
+dW, db, ev = bk.weight_grad_views(6, 4)
+assert ev is None and dW.shape == (6, 4) and db.shape == (6,) and dW.data_ptr() == bk.flat.data_ptr()
+dW.fill_(float(rank + 1)); db.fill_(2.0 * (rank + 1)); bk.extra_slice.fill_(4.0 * (rank + 1))
+bk.weight_grads_enqueued()           # joint slice reduced early ...
+flat = bk.finish()                   # ... the rest + averaging at the end of the step
+assert torch.allclose(flat[:24], torch.full((24,), 1.5)) and torch.allclose(flat[24:30], torch.full((6,), 3.0))
+assert torch.allclose(flat[30:], torch.full((5,), 6.0)) and not bk.pending
+dW.fill_(float(rank + 1)); db.fill_(0.0); bk.extra_slice.fill_(0.0)
+flat = bk.finish()                   # no fused backward fed the bucket: finish() reduces everything
+assert torch.allclose(flat[:24], torch.full((24,), 1.5))
 dist.destroy_process_group()
 print("ok", rank)
 """
