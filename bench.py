@@ -367,7 +367,7 @@ def run_gpu_arm(args):
     cells_rank = Bg * T * (U + 1)
 
     def make_sets(b, n_sets=3):   # rotating input sets: >= 3 x 70 MB > 126 MB L2, so inputs are L2-cold every step
-        sets = [synth_inputs(torch, 1234 + rank * 16 + i, dev, b=b) for i in range(n_sets)]
+        sets = [synth_inputs(torch, 1234 + rank * 16 + i, dev, b=b, view=not args.dense_encoder) for i in range(n_sets)]
         for s_ in sets:
             for k in ("enc", "pred", "W", "b"):
                 s_[k].requires_grad_(True)
@@ -462,7 +462,7 @@ def run_gpu_arm(args):
     # ---- e2e: same step through the public API from pinned HOST buffers, result read back to host.
     # Every step copies that step's inputs host->device (all 7 tensors) and reads its loss back; the copy of
     # step i+1 runs on a side stream into the other device buffer while step i computes (double buffering).
-    host = synth_inputs(torch, 4321 + rank, dev, b=Bg, pin=True)
+    host = synth_inputs(torch, 4321 + rank, dev, b=Bg, pin=True, view=not args.dense_encoder)
     devbufs = []
     for _ in range(2):
         d = {k: torch.empty_like(v, device=dev) for k, v in host.items()}      # keeps the (B,H,T)-view strides of enc
@@ -585,7 +585,8 @@ def run_gpu_arm(args):
                                 parallelism=(f"dp{world} by utterance; dW/db written into one flat bucket, NCCL "
                                              f"all-reduce of {V * H + V} joint + {PRED_GRAD_ELEMS} predictor(stub) fp32 "
                                              "grads, the joint part overlapped with the dh GEMM") if world > 1 else "single GPU",
-                                encoder_layout="(B,T,H) view of a (B,H,T) tensor (rnnt/model.py:28), read in place",
+                                encoder_layout=("dense (B,T,H) tensor (--dense-encoder)" if args.dense_encoder else
+                                                "(B,T,H) view of a (B,H,T) tensor (rnnt/model.py:28), read in place"),
                                 l2=f"3 rotating input sets ({3 * 70 * Bg // 32} MB > 126 MB L2); every step also streams the "
                                    "fp16 activation residual and the gradient ring through HBM",
                                 operands="fp16 x fp16 -> fp32 (TMEM), fp32 elsewhere",
@@ -637,6 +638,8 @@ def main():
                     help="N>1: global batch sharded over the GPUs (BASELINE configs[2]); 0 = weak scaling, B=32 per GPU")
     ap.add_argument("--sustain-s", type=float, default=3.0,
                     help="N=1: length of the extra sustained (power-capped) loop in seconds; 0 disables")
+    ap.add_argument("--dense-encoder", action="store_true",
+                    help="feed a dense (B,T,H) encoder tensor instead of the (B,H,T) view the reference model produces")
     ap.add_argument("--all-tiles", action="store_true",
                     help="backward processes every half-tile of the lattice (also those whose fp16 gradients are all zero)")
     args = ap.parse_args()

@@ -130,6 +130,18 @@ int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, co
                             int max_per_frame, int32_t* tokens, int32_t* n_tokens, float* margins_out, void* scratch,
                             void* stream);
 
+/* Optional pre-projections of the joint (rnnt/joint.py:8-12, 26-30: audio_ln / text_ln of the non-"convjs" configs) as
+ * tcgen05 GEMMs ahead of the fused call, with their backward.  Row-major contiguous fp32 tensors:
+ *   fwd:  y[M,N] = x[M,K] . W[N,K]^T + bias[N]        (M = B*T or B*U1 rows, K = in features, N = hidden_features)
+ *   bwd:  dx[M,K] = dy . W,  dW[N,K] = dy^T . x,  db[N] = column sums of dy;  any of dx / dW / db may be NULL (skipped)
+ * Operands are rounded to fp16, accumulation is fp32.  K and N must be multiples of 8.  flags: RNNT_B200_DETERMINISTIC.
+ * workspace: rnnt_b200_linear_workspace_bytes(M, K, N, backward, flags) bytes, 256-byte aligned. */
+size_t rnnt_b200_linear_workspace_bytes(int64_t M, int K, int N, int backward, int flags);
+int rnnt_b200_linear_fwd(const float* x, const float* W, const float* bias, int64_t M, int K, int N, float* y,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int rnnt_b200_linear_bwd(const float* x, const float* W, const float* dy, int64_t M, int K, int N, float* dx,
+                         float* dW, float* db, int flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Opt-in measurement hook (bench.py): between begin and end every kernel launch of the library is bracketed by
  * CUDA events on its launch stream.  end() synchronises on those events and returns, per kernel family, the summed
  * device time in ms and the number of launches.  HOST pointers.  Families: 0 prep (tile table, weight conversion,

@@ -375,6 +375,42 @@ int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, co
   return rb::launch_greedy_decode(a, static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));
 }
 
+size_t rnnt_b200_linear_workspace_bytes(int64_t M, int K, int N, int backward, int flags) {
+  if (M <= 0 || K <= 0 || N <= 0) return 0;
+  return rb::linear_workspace_bytes(M, K, N, backward != 0, (flags & RNNT_B200_DETERMINISTIC) != 0);
+}
+
+namespace {
+int check_linear(const void* x, const void* W, int64_t M, int K, int N, const void* workspace, size_t workspace_bytes,
+                 size_t need) {
+  RB_REQUIRE(M > 0 && M < (1ll << 31) && K > 0 && N > 0, -1, "invalid shape M=%lld K=%d N=%d", (long long)M, K, N);
+  RB_REQUIRE(K % 8 == 0 && N % 8 == 0, -2, "pre-projection: in/out features must be multiples of 8 (got %d, %d)", K, N);
+  RB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0, -3,
+             "pre-projection: x / W must be 16-byte aligned");
+  RB_REQUIRE(workspace != nullptr && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, -7,
+             "pre-projection: workspace must be 256-byte aligned and hold %zu bytes", need);
+  return 0;
+}
+}  // namespace
+
+int rnnt_b200_linear_fwd(const float* x, const float* W, const float* bias, int64_t M, int K, int N, float* y,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_linear(x, W, M, K, N, workspace, workspace_bytes, rb::linear_workspace_bytes(M, K, N, false, false));
+  if (rc) return rc;
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, -3, "pre-projection: y must be 16-byte aligned");
+  return rb::launch_linear_fwd(x, W, bias, M, K, N, y, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int rnnt_b200_linear_bwd(const float* x, const float* W, const float* dy, int64_t M, int K, int N, float* dx,
+                         float* dW, float* db, int flags, void* workspace, size_t workspace_bytes, void* stream) {
+  const bool det = (flags & RNNT_B200_DETERMINISTIC) != 0;
+  int rc = check_linear(x, W, M, K, N, workspace, workspace_bytes, rb::linear_workspace_bytes(M, K, N, true, det));
+  if (rc) return rc;
+  RB_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dW)) & 15) == 0,
+             -3, "pre-projection: dy / dx / dW must be 16-byte aligned");
+  return rb::launch_linear_bwd(x, W, dy, M, K, N, dx, dW, db, det, workspace, static_cast<cudaStream_t>(stream));
+}
+
 int rnnt_b200_profile_begin(void) { return rb::prof_begin(); }
 int rnnt_b200_profile_end(float* ms, int64_t* launches) {
   long long l[rb::kProfFamilies];

@@ -138,4 +138,11 @@ int launch_joint_argmax(const float* enc_rows, long long enc_stride, const float
                         float* scratch, cudaStream_t stream);
 size_t joint_argmax_scratch_bytes(int N, int V);
 
+// pre-projection GEMMs (linear_gemm.cu): y = x W^T + b and its backward, fp16 operands / fp32 accumulate
+size_t linear_workspace_bytes(long long M, int K, int N, bool backward, bool deterministic);
+int launch_linear_fwd(const float* x, const float* W, const float* bias, long long M, int K, int N, float* y,
+                      void* workspace, cudaStream_t stream);
+int launch_linear_bwd(const float* x, const float* W, const float* dy, long long M, int K, int N, float* dx, float* dW,
+                      float* db, bool deterministic, void* workspace, cudaStream_t stream);
+
 }  // namespace rb

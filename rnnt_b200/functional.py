@@ -202,6 +202,57 @@ class _FusedJointLoss(torch.autograd.Function):
         return d_enc, d_pred, dW, db, None, None, None, None, None, None, None, None, None
 
 
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b through the library's tcgen05 GEMM (fp16 operands, fp32 accumulate), with its backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        L = _lib.lib()
+        K, N = weight.shape[1], weight.shape[0]
+        x2 = x.reshape(-1, K).contiguous()
+        w = weight.contiguous()
+        M = x2.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        nbytes = L.rnnt_b200_linear_workspace_bytes(M, K, N, 0, 0)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.rnnt_b200_linear_fwd(x2.data_ptr(), w.data_ptr(), bias.contiguous().data_ptr(), M, K, N,
+                                              y.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr(x.device)), "linear_fwd")
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(M, N).contiguous().float()
+        flags = _lib.FLAG_DETERMINISTIC if (_DETERMINISTIC or torch.are_deterministic_algorithms_enabled()) else 0
+        dx = torch.empty(M, K, dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[0] else None
+        dW = torch.empty(N, K, dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[1] else None
+        db = torch.empty(N, dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[2] else None
+        nbytes = L.rnnt_b200_linear_workspace_bytes(M, K, N, 1, flags)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(dy.device):
+            _lib.check(L.rnnt_b200_linear_bwd(x2.data_ptr(), w.data_ptr(), dy2.data_ptr(), M, K, N, ptr(dx), ptr(dW),
+                                              ptr(db), flags, ws.data_ptr(), nbytes, _stream_ptr(dy.device)),
+                       "linear_bwd")
+        return (dx.view(ctx.x_shape) if dx is not None else None), dW, db
+
+
+def linear(x, weight, bias):
+    """The joint's pre-projection (rnnt/joint.py:26-30 `audio_ln` / `text_ln`) as a tcgen05 GEMM of this library.
+    fp32 CUDA tensors with in / out features that are multiples of 8 run the kernels; anything else is not part of
+    the hot path and goes through torch's own linear."""
+    if (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and bias is not None
+            and weight.shape[0] % 8 == 0 and weight.shape[1] % 8 == 0 and x.numel() > 0):
+        return _Linear.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 def _reduce(costs, reduction):
     if reduction == "none":
         return costs

@@ -48,11 +48,16 @@ class JointNetwork(torch.nn.Module):
         self.blank_idx = num_classes - 1
         self.zero_edit_mode = False
 
-    def _project(self, audio_frame, text_frame):
+    def _project(self, audio_frame, text_frame, fused: bool = False):
+        """rnnt/joint.py:26-30.  fused=True (the loss path): the projections run as tcgen05 GEMMs of the library."""
+        if fused:
+            from .functional import linear
+        else:
+            linear = F.linear
         if hasattr(self, "audio_ln"):
-            audio_frame = self.audio_ln(audio_frame)
+            audio_frame = linear(audio_frame, self.audio_ln.weight, self.audio_ln.bias)
         if hasattr(self, "text_ln"):
-            text_frame = self.text_ln(text_frame)
+            text_frame = linear(text_frame, self.text_ln.weight, self.text_ln.bias)
         return audio_frame, text_frame
 
     def forward(self, audio_frame, text_frame):
@@ -60,8 +65,9 @@ class JointNetwork(torch.nn.Module):
 
         In zero-edit mode with grad enabled this returns a LazyJointLogits handle for the patched
         torchaudio.functional.rnnt_loss; the dense result is only meant for small shapes."""
-        audio_frame, text_frame = self._project(audio_frame, text_frame)
-        if self.zero_edit_mode and torch.is_grad_enabled() and audio_frame.is_cuda:
+        lazy = self.zero_edit_mode and torch.is_grad_enabled() and audio_frame.is_cuda
+        audio_frame, text_frame = self._project(audio_frame, text_frame, fused=lazy)
+        if lazy:
             return LazyJointLogits(audio_frame, text_frame, self.joint_ln.weight, self.joint_ln.bias)
         joint_frames = self.activation(audio_frame.unsqueeze(2) + text_frame.unsqueeze(1))
         return self.joint_ln(joint_frames)
@@ -76,7 +82,7 @@ class JointNetwork(torch.nn.Module):
         """Fused forward + transducer loss: replaces `joint(...)` + `torchaudio.functional.rnnt_loss(...)`
         (rnnt/model.py:32-41) without creating the logits.  Gradients reach every parameter through autograd."""
         from .functional import joint_rnnt_loss
-        audio_frame, text_frame = self._project(audio_frame, text_frame)
+        audio_frame, text_frame = self._project(audio_frame, text_frame, fused=True)
         return joint_rnnt_loss(audio_frame, text_frame, self.joint_ln.weight, self.joint_ln.bias, targets,
                                logit_lengths, target_lengths, blank=blank, clamp=clamp, reduction=reduction,
                                validate=validate)

@@ -786,3 +786,110 @@ def test_greedy_decode_dispatches_on_predictor_shape():
     assert one == got[0]
     with pytest.raises(ValueError, match="Unknown predictor type"):
         rnnt_b200.RNNTModel(torch.nn.Linear(2, 2), torch.nn.Identity(), joint).cuda().greedy_decode_features(feats, lens)
+
+
+@pytest.mark.parametrize("shape", [(12800, 1024, 1024), (404, 1024, 1024), (300, 72, 136), (1, 8, 8), (77, 40, 264),
+                                   (2600, 256, 128)])
+def test_preprojection_gemm_matches_torch(shape):
+    """rnnt_b200_linear_fwd/bwd (tcgen05, fp16 operands) vs torch fp32 linear: y, dx, dW, db; ragged tile edges."""
+    from rnnt_b200.functional import linear
+    M, K, N = shape
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).cuda().requires_grad_(True)
+    W = ((torch.rand(N, K, generator=g) * 2 - 1) / K ** 0.5).cuda().requires_grad_(True)
+    b = ((torch.rand(N, generator=g) * 2 - 1) / K ** 0.5).cuda().requires_grad_(True)
+    dy = torch.randn(M, N, generator=g).cuda()
+    y = linear(x, W, b)
+    y.backward(dy)
+    got = [y.detach(), x.grad.clone(), W.grad.clone(), b.grad.clone()]
+    x.grad = W.grad = b.grad = None
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        y2 = torch.nn.functional.linear(x, W, b)
+        y2.backward(dy)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    for name, a, r in zip(("y", "dx", "dW", "db"), got, (y2.detach(), x.grad, W.grad, b.grad)):
+        assert rel_err(a, r)[0] < 1e-3, (shape, name, rel_err(a, r))
+    # deterministic variant of the split-K weight gradient
+    torch.use_deterministic_algorithms(True)
+    try:
+        outs = []
+        for _ in range(2):
+            x.grad = W.grad = b.grad = None
+            linear(x, W, b).backward(dy)
+            outs.append((W.grad.clone(), b.grad.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        assert rel_err(outs[0][0], got[2])[0] < 1e-5
+    finally:
+        torch.use_deterministic_algorithms(False)
+
+
+def test_preprojection_joint_full_width_vs_reference():
+    """f-4 at the reference's width: JointNetwork(audio_features=1024, text_features=1024, 1024, 1024) -- the joint of the
+    non-"convjs" configs -- loss and every gradient (raw inputs, audio_ln, text_ln, joint_ln) vs the same modules run
+    the reference's way (torch fp32 linear + tanh + torchaudio rnnt_loss) on the same device."""
+    import torchaudio
+    import rnnt_b200
+    torch.manual_seed(7)
+    B, T, U, F_, H, V = 4, 120, 30, 1024, 1024, 1024
+    joint = rnnt_b200.JointNetwork(F_, F_, H, V).cuda()
+    audio = torch.randn(B, T, F_, device="cuda")
+    text = torch.randn(B, U + 1, F_, device="cuda")
+    targets = torch.randint(0, V - 1, (B, U), dtype=torch.int32, device="cuda")
+    T_len = torch.tensor([T, T - 7, T // 2, T], dtype=torch.int32, device="cuda")
+    U_len = torch.tensor([U, U // 2, U, 3], dtype=torch.int32, device="cuda")
+
+    def run(fused):
+        a = audio.clone().requires_grad_(True)
+        t = text.clone().requires_grad_(True)
+        joint.zero_grad()
+        if fused:
+            costs = joint.loss(a, t, targets, T_len, U_len, reduction="none")
+        else:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                costs = torchaudio.functional.rnnt_loss(joint(a, t), targets, T_len, U_len, blank=-1, clamp=-1,
+                                                        reduction="none")
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        costs.sum().backward()
+        grads = {n: p.grad.clone() for n, p in joint.named_parameters()}
+        grads["audio"], grads["text"] = a.grad, t.grad
+        return costs.detach(), grads
+
+    c_ref, g_ref = run(False)
+    c_our, g_our = run(True)
+    assert ((c_our - c_ref).abs() <= LOSS_RTOL * c_ref.abs()).all(), (c_our, c_ref)
+    for k in g_ref:
+        assert rel_err(g_our[k], g_ref[k])[0] <= GRAD_TOL_FP32, (k, rel_err(g_our[k], g_ref[k]))
+
+
+def test_train_loop_guard_shapes_fit_in_bounded_memory():
+    """f-3: rnnt/train.py:120-130 halves any batch with max(U) * max(mel frames) > max_joint_size (160,000 in the shipped
+    configs) because the (B,T,U+1,V) logits, their gradients and the fp32 activations would not fit a 24 GB card.
+    A batch 5.6x over that limit (U=300, 3000 mel frames -> T=1500, B=8: the reference would need 14.8 GB logits +
+    14.8 GB logit-gradients + 14.8 GB activations) runs fused forward+backward in a few GiB, so the guard (and its two
+    `.item()` syncs per step) can be dropped by the owner."""
+    import rnnt_b200
+    B, T, U, H, V = 8, 1500, 300, 1024, 1024
+    assert U * (2 * T) > 160000 * 5
+    inp = make_inputs(B, T, U, H, V, ragged=True, seed=8)
+    peaks = {}
+    for save_hidden in (True, False):
+        enc = inp["enc"].clone().requires_grad_(True)
+        W = inp["W"].clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        loss = rnnt_b200.joint_rnnt_loss(enc, inp["pred"], W, inp["b"], inp["targets"], inp["T_len"], inp["U_len"],
+                                         reduction="mean", save_hidden=save_hidden)
+        loss.backward()
+        torch.cuda.synchronize()
+        peaks[save_hidden] = (torch.cuda.max_memory_allocated() - base) / 2 ** 30
+        assert torch.isfinite(loss.detach()) and torch.isfinite(enc.grad).all() and torch.isfinite(W.grad).all()
+        del loss, enc, W
+    reference_need = 3 * B * T * (U + 1) * V * 4 / 2 ** 30      # logits + logit-gradients + fp32 activations (H = V)
+    assert reference_need > 40 and peaks[True] < 12 and peaks[False] < 5, (reference_need, peaks)
