@@ -418,7 +418,9 @@ def run_gpu_arm(args):
             _lib.check(L.rnnt_b200_profile_end(fam_ms, fam_n), "profile_end")
         clocks = sampler.stop() if (sample_clocks and rank == 0) else None
         nccl_ms = bucket.collective_ms() / nsteps if bucket is not None else 0.0
-        return dict(ms=ms, fam_ms=list(fam_ms), fam_n=list(fam_n), clocks=clocks, last=last, nccl_ms=nccl_ms)
+        exposed_ms = bucket.exposed_ms() / nsteps if bucket is not None else 0.0
+        return dict(ms=ms, fam_ms=list(fam_ms), fam_n=list(fam_n), clocks=clocks, last=last, nccl_ms=nccl_ms,
+                    exposed_ms=exposed_ms)
 
     for i in range(args.warmup):
         step(sets[i % len(sets)])
@@ -508,11 +510,11 @@ def run_gpu_arm(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- max over ranks
-    times = torch.tensor([ms_total, e2e_s * 1e3, dense_ms or 0.0, weak_ms or 0.0, head["nccl_ms"]], dtype=torch.float64,
-                         device=dev)
+    times = torch.tensor([ms_total, e2e_s * 1e3, dense_ms or 0.0, weak_ms or 0.0, head["nccl_ms"], head["exposed_ms"]],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, dense_ms, weak_ms, nccl_ms = (float(x) for x in times)
+    ms_total, e2e_ms, dense_ms, weak_ms, nccl_ms, exposed_ms = (float(x) for x in times)
 
     if rank == 0:
         peaks = load_peaks()
@@ -608,9 +610,12 @@ def run_gpu_arm(args):
                                if dense_ms else None),
                     roofline=roofline)
         if world > 1:
-            line["nccl"] = dict(ms_per_step=nccl_ms, bytes_per_step=4 * (V * H + V + PRED_GRAD_ELEMS),
-                                note="device time of the step's NCCL all-reduces (events on the side stream, max over "
-                                     "ranks); the joint bucket's share runs under the dh GEMM")
+            line["nccl"] = dict(exposed_ms_per_step=exposed_ms, in_flight_ms_per_step=nccl_ms,
+                                bytes_per_step=4 * (V * H + V + PRED_GRAD_ELEMS),
+                                note="exposed = time the compute stream stalls for the collectives at the end of the "
+                                     "step (CUDA events, max over ranks); in_flight = enqueue-to-completion of the "
+                                     "all-reduces on the side stream (the joint bucket's is gated by the dW-done event "
+                                     "and shares the SMs with the dh GEMM, so it includes waiting for SM resources)")
         if weak_ms:
             line["weak_b32_per_gpu"] = dict(ms_per_step=weak_ms, value=B * T * (U + 1) * world / (weak_ms * 1e-3),
                                             unit=UNIT, global_batch=B * world,

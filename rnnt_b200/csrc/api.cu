@@ -306,6 +306,8 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
     d.slot_begin = slot_begin; d.slot_cap = static_cast<int>(ring_slots);
     d.d_enc = d_enc; d.denc_sb = denc_sb; d.denc_st = denc_st; d.denc_sh = denc_sh; d.d_pred = d_pred;
     d.d_enc_fx = fx_enc; d.d_pred_fx = fx_pred;
+    // with a dW-done event the caller is about to run a collective next to this kernel: leave it a few SMs
+    { const char* e = getenv("RNNT_B200_COMM_SMS"); d.spare_pairs = (dw_done_event && c == nchunks - 1) ? (e ? atoi(e) : 0) / 2 : 0; }
     rc = rb::launch_dh_gemm(tmG128, tmWmn, d, chunk_slots, stream);
     if (rc) return rc;
   }

@@ -59,6 +59,7 @@ struct DhArgs {
   // dense (B,T,H) / (B,U1,H) row-major, converted to d_enc / d_pred by finalize_fixed_kernel
   long long* d_enc_fx;
   long long* d_pred_fx;
+  int spare_pairs;       // CTA pairs (2 SMs each) the launch leaves idle so that a concurrent NCCL kernel finds SMs
 };
 
 struct DwArgs {

@@ -56,6 +56,7 @@ class WeightGradBucket:
         self.pending = False
         self.time_collectives = False      # bench.py: bracket every collective with CUDA events on the side stream
         self._timing = []
+        self._exposed = []
 
     @property
     def joint_slice(self):
@@ -80,6 +81,12 @@ class WeightGradBucket:
 
     def reset_timing(self):
         self._timing = []
+        self._exposed = []
+
+    def exposed_ms(self) -> float:
+        """Summed time the compute stream waited in finish() since reset_timing() (synchronises)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in self._exposed))
 
     def collective_ms(self) -> float:
         """Summed device time of the all-reduces since reset_timing() (synchronises)."""
@@ -128,7 +135,14 @@ class WeightGradBucket:
             if self.average:
                 self.flat.div_(world)
         if self.stream is not None:
-            cur.wait_stream(self.stream)
+            if self.time_collectives:      # how long the compute stream stalls for the collectives = their EXPOSED time
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(cur)
+                cur.wait_stream(self.stream)
+                b.record(cur)
+                self._exposed.append((a, b))
+            else:
+                cur.wait_stream(self.stream)
         self.pending = False
         return self.flat
 
