@@ -371,7 +371,7 @@ int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, co
   a.Wj = joint_w; a.bj = joint_b; a.emb = emb; a.ln1_w = ln1_w; a.ln1_b = ln1_b;
   a.w1 = conv1_w; a.b1 = conv1_b; a.w2 = conv2_w; a.b2 = conv2_b; a.wl = lin_w; a.bl = lin_b;
   a.ln2_w = ln2_w; a.ln2_b = ln2_b;
-  a.B = B; a.T = T; a.H = H; a.V = V; a.E = E; a.blank = blank; a.max_len = max_len;
+  a.B = B; a.T = T; a.H = H; a.V = V; a.E = E; a.NS = V; a.blank = blank; a.max_len = max_len;
   a.max_per_frame = max_per_frame; a.max_steps = T + max_len + 1;
   a.tokens = tokens; a.ntok = n_tokens; a.margins = margins_out;
   return rb::launch_greedy_decode(a, static_cast<float*>(scratch), static_cast<cudaStream_t>(stream));

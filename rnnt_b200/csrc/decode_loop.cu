@@ -8,13 +8,15 @@
 // embeddings (conv1, k=3) and the last 4 conv1 outputs (conv2, k=5) are kept and one new position is computed per
 // emitted token; zero-initialised state is the left zero padding of rnnt/causalconv.py:29.
 //
-// One CTA per SM, 256 threads, phases separated by grid-wide barriers:
+// One CTA per SM, 256 threads, phases separated by grid-wide barriers (the kernel's own counter barrier; the launch is
+// cooperative so that all CTAs are co-resident).  Every weight matrix is split by output over the CTAs and each CTA's
+// slice lives in shared memory for the whole decode, so a step only moves activations:
 //   P1  feats = LayerNorm(lin) for utterances that just emitted; h = tanh(enc[b, t_b] + feats[b])
-//   P2  logits[b, v] = W_j[v,:] . h[b,:] + b_j[v]        (CTA per 8 classes, K split over the threads, see batched_gemv)
-//   P3  argmax (lowest index on ties) + top-2 margin, blank / max-per-frame rule, token append, x = LN(emb[tok])
-//   P4  y = gelu(conv1 tap-GEMV)   P5  z = gelu(conv2 tap-GEMV), shift conv1 state   P6  lin = linear(z), shift conv2 state
+//   P2  logits[b, v] = W_j[v,:] . h[b,:] + b_j[v]        (CTA = its ~V/148 classes, warp = 4 rows, lanes split K; gemv_phase)
+//   P3  argmax (lowest index on ties) + top-2 margin, blank / max-per-frame rule, token append
+//   P4  y = gelu(conv1) from the tap products of x = LN(emb[tok]) (table)   P5  z = gelu(conv2) likewise   P6  lin = linear(z)
 // P4-P6 only run in steps where some utterance emitted.  Every dot product is accumulated in a fixed order (thread-
-// strided partial sums, butterfly, then warps 0..7), so results are deterministic.
+// strided partial sums, then one fixed warp butterfly), so results are deterministic.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -63,33 +65,25 @@ __device__ void block_layer_norm(const float* __restrict__ src, const float* __r
   for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = (src[i] - mean) * rstd * w[i] + b[i];
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-
-// out[r, o] = act(bias[o] + W[o, :] . in_r) for the rows r listed in `rows` (nrows of them), o in [0, nout).
-// in_r is the concatenation of up to two row segments; W is (nout, klen) row-major, klen a multiple of 4.
-//
-// A CTA task = OUT consecutive outputs.  The 256 threads split K (thread t takes float4 t, t+256, ...), so every
-// activation element is read from shared memory ONCE per CTA (not once per warp); each thread keeps OUT x kRows
-// partial sums, a warp transpose-reduce leaves lane l with the warp total of partial l, and one pass over
-// partial[warp][l] in shared memory finishes the sum.  Activation rows are staged kRows at a time with cp.async into
-// a double buffer so the next chunk streams in from L2 while the current one is being multiplied.
-struct Seg { const float* base; long long row_stride; int len; };
-
-constexpr int kRows = 8;
-constexpr int kMaxIt = 3;   // float4 K-steps per thread: supports K <= 4 * 3 * 256 = 3072
-
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending(int n) {   // at most n most-recent groups still in flight
-  switch (n) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-  }
-}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batched GEMV of one phase: out[r, o] = act(bias[o] + W[o, :] . in_r) for the rows r listed in `rows`, o in the
+// CTA's own output range [o_lo, o_hi).  in_r is the concatenation of up to two row segments (lengths multiples of 4).
+//
+// Every weight matrix is split BY OUTPUT over the CTAs and the CTA's slice stays in shared memory for the whole decode
+// (14.7 MB of fp32 weights / 148 SMs = 99 KB per SM at H = V = 1024, E = 512), so a step only moves activations.  A warp
+// owns groups of kRG rows: lane l accumulates, for each of its rows and up to kOB outputs, the float4 columns
+// l, l + 32, ... of the dot products (activations straight from L2 with coalesced 16-byte loads, weights from shared
+// memory), then ONE warp transpose-reduce turns the kRG x kOB per-lane partials into totals -- no block barrier, no
+// staging buffer, fixed summation order.
+constexpr int kRG = 4;    // rows per warp pass
+constexpr int kOB = 8;    // outputs per accumulator block
+constexpr int kJ = 4;     // float4 columns per lane and row in flight (K = 512 phases: the whole row)
 
 // v[32] per lane -> lane l returns the sum over the warp's lanes of v[l] (31 shuffles instead of 32 x 5).
 __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
@@ -107,214 +101,280 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
   return v[0];
 }
 
-template <bool GELU, int OUT>
-__device__ void batched_gemv(const float* __restrict__ W, const float* __restrict__ bias, int nout, int klen,
-                             const Seg* segs, int nsegs, const int* __restrict__ rows, int nrows,
-                             float* __restrict__ out, long long out_stride, float* smem, int smem_floats,
-                             float* partial, int rsplit = 1) {
-  static_assert(OUT * kRows == 32 || OUT * kRows == 64, "partial sums per thread must be 32 or 64");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k4 = klen >> 2;
-  // a task = OUT outputs x one of `rsplit` ranges of row chunks (more tasks than SMs would cost a second wave, fewer
-  // leave SMs idle: the callers pick OUT and rsplit so that ntasks is just under the grid size)
-  const int ntasks = ((nout + OUT - 1) / OUT) * rsplit;
-  const int nchunks_all = (nrows + kRows - 1) / kRows;
-  const int chunks_per_part = (nchunks_all + rsplit - 1) / rsplit;
-  const int depth = max(2, min(4, smem_floats / (kRows * klen)));   // staging ring: chunks c .. c+depth-1 in flight
+// EPI 0: out[row][o] = bias[o] + dot            (joint logits, linear)
+// EPI 1: causal-conv tap accumulation.  The CTA's outputs are "virtual": vo = (o - o_lo) * taps + j is the dot product of
+//        tap j of output channel o (row o of the (E, taps*E) weight, columns [j E, (j+1) E)) with the NEW input vector
+//        only.  A causal conv of kernel size `taps` at position n is  y_n = gelu(b + sum_j W_j x_{n-taps+1+j}), so the
+//        new vector x_n contributes W_j x_n to position n + taps-1 - j: those partial sums live in a per-utterance
+//        ring acc[row][taps][E] (zero-initialised = the left zero padding of rnnt/causalconv.py:29).  The newest tap
+//        completes position n: out[row][o] = gelu(bias[o] + acc[row][n % taps][o] + dot) and the slot is cleared for
+//        position n + taps.  A step therefore reads E instead of taps*E activations per utterance.
+struct GemvEpi {
+  int mode;                 // 0 / 1 as above
+  int taps;                 // EPI 1
+  float* acc;               // EPI 1: [B][taps][E]
+  const int* npos;          // EPI 1: position counter source: n = npos[row] - 1
+  int E;
+};
 
-  auto stage = [&](int chunk, float* dst) {
-    const int r0 = chunk * kRows, nr = min(kRows, nrows - r0);
-    for (int rr = 0; rr < nr; ++rr) {
-      const int r = rows[r0 + rr];
-      int off = 0;
-      for (int sg = 0; sg < nsegs; ++sg) {
-        const float* src = segs[sg].base + r * segs[sg].row_stride;
-        for (int i = tid; i < (segs[sg].len >> 2); i += kThreads) cp_async16(dst + rr * klen + off + 4 * i, src + 4 * i);
-        off += segs[sg].len;
+template <bool GELU>
+__device__ void gemv_phase(const float* Wslice /* rows o_lo.. of W, shared or global */, const float* __restrict__ bias,
+                           int o_lo, int o_hi, int K, int w_ld, const float* src, long long src_stride,
+                           const int* src_index /* optional: source row = src_index[row] */, const int* rows, int nrows,
+                           float* __restrict__ out, long long out_stride, GemvEpi epi, float* xstage) {
+  if (o_lo >= o_hi) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K4 = K >> 2;
+  const int nchunks = (K4 + 32 * kJ - 1) / (32 * kJ);
+  // this warp's private staging buffer: kRG rows x (32 kJ) float4.  The group's activations travel L2 -> shared memory
+  // with cp.async (no registers held while in flight) once per row group when one chunk covers K, and every output
+  // block then reads them from shared memory instead of paying another exposed L2 round trip.
+  float4* xs = reinterpret_cast<float4*>(xstage) + warp * (kRG * 32 * kJ);
+  const int taps = epi.mode == 1 ? epi.taps : 1;
+  const int nvirt = (o_hi - o_lo) * taps;
+  for (int g = warp; g * kRG < nrows; g += kThreads / 32) {
+    int rid[kRG];
+    long long soff[kRG];
+#pragma unroll
+    for (int r = 0; r < kRG; ++r) {
+      rid[r] = __ldcg(rows + min(g * kRG + r, nrows - 1));        // tail rows repeat the last one
+      soff[r] = static_cast<long long>(src_index ? __ldcg(src_index + rid[r]) : rid[r]) * src_stride;
+    }
+    // activations are produced by other CTAs during this kernel: read them through L2 (ld.global.cg), never L1
+    // activations are produced by other CTAs during this kernel: they are read through L2 (cp.async.cg), never L1
+    auto stage_x = [&](int c) {
+      __syncwarp();                                   // everybody is done reading the previous contents
+#pragma unroll
+      for (int r = 0; r < kRG; ++r)
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) {
+          const int f = (c * kJ + j) * 32 + lane;
+          if (f < K4) cp_async16(xs + (r * kJ + j) * 32 + lane, reinterpret_cast<const float4*>(src + soff[r]) + f);
+        }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+    };
+    if (nchunks == 1) stage_x(0);
+    for (int vb = 0; vb < nvirt; vb += kOB) {
+      float acc[kRG * kOB];
+#pragma unroll
+      for (int q = 0; q < kRG * kOB; ++q) acc[q] = 0.f;
+      // epilogue operand of this lane's (row, output): requested now, its L2 round trip hides under the FMAs
+      const int er = lane / kOB, evo = vb + lane % kOB;
+      const bool e_ok = g * kRG + er < nrows && evo < nvirt;
+      float* slot = nullptr;
+      float prev = 0.f;
+      if (epi.mode == 1 && e_ok) {
+        int erow = rid[0];
+#pragma unroll
+        for (int r = 1; r < kRG; ++r) erow = (er == r) ? rid[r] : erow;
+        const int n = __ldcg(epi.npos + erow) - 1;               // position of the new input vector
+        slot = epi.acc + (static_cast<long long>(erow) * taps + (n + taps - 1 - evo % taps) % taps) * epi.E + o_lo + evo / taps;
+        prev = __ldcg(slot);                                     // only this CTA ever touches (row, *, o)
       }
-    }
-    cp_async_commit();
-  };
-
-  for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-    const int o0 = (task / rsplit) * OUT;
-    const int c_lo = (task % rsplit) * chunks_per_part;
-    const int nchunks = min(nchunks_all, c_lo + chunks_per_part) - c_lo;   // chunks c_lo .. c_lo + nchunks - 1
-    if (nchunks <= 0) continue;         // uniform over the CTA
-    const float4* w4[OUT];
+      for (int f0 = 0; f0 < K4; f0 += 32 * kJ) {
+        if (nchunks > 1) stage_x(f0 / (32 * kJ));
+        float4 x[kRG][kJ];        // (live inside one output block only: kept across blocks, ptxas spills 4 KB)
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) w4[o] = reinterpret_cast<const float4*>(W + static_cast<long long>(min(o0 + o, nout - 1)) * klen);
-    __syncthreads();                    // previous users of the staging buffers are done
-    for (int c = 0; c < depth - 1; ++c) {
-      if (c < nchunks) stage(c_lo + c, smem + (c % depth) * kRows * klen); else cp_async_commit();
-    }
-    // this thread's slice of the OUT weight rows stays in registers for the whole task (K <= 3072)
-    float4 wreg[kMaxIt][OUT];
+        for (int r = 0; r < kRG; ++r)
 #pragma unroll
-    for (int it = 0; it < kMaxIt; ++it) {
-      const int i = tid + it * kThreads;
+          for (int j = 0; j < kJ; ++j) {
+            const int f = f0 + j * 32 + lane;
+            x[r][j] = f < K4 ? xs[(r * kJ + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-      for (int o = 0; o < OUT; ++o) wreg[it][o] = (i < k4) ? __ldg(w4[o] + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int c = 0; c < nchunks; ++c) {
-      const int r0 = (c_lo + c) * kRows, nr = min(kRows, nrows - r0);
-      const int ahead = c + depth - 1;    // one commit per iteration keeps the group count uniform
-      if (ahead < nchunks) stage(c_lo + ahead, smem + (ahead % depth) * kRows * klen); else cp_async_commit();
-      cp_async_wait_pending(depth - 1);
-      __syncthreads();                  // chunk c has landed for every thread
-      const float4* x4 = reinterpret_cast<const float4*>(smem + (c % depth) * kRows * klen);
-      float acc[OUT * kRows];
+        for (int o = 0; o < kOB; ++o) {
+          const int vo = vb + o;
+          if (vo < nvirt) {         // uniform
+            // virtual output vo -> weight row (vo / taps) of the slice, column block (vo % taps) * K
+            const float4* w4 = reinterpret_cast<const float4*>(Wslice + static_cast<long long>(vo / taps) * w_ld +
+                                                               static_cast<long long>(vo % taps) * K);
 #pragma unroll
-      for (int q = 0; q < OUT * kRows; ++q) acc[q] = 0.f;
+            for (int j = 0; j < kJ; ++j) {
+              const int f = f0 + j * 32 + lane;
+              if (f < K4) {
+                const float4 w = w4[f];
 #pragma unroll
-      for (int it = 0; it < kMaxIt; ++it) {
-        const int i = tid + it * kThreads;
-        if (i < k4) {
-#pragma unroll
-          for (int rr = 0; rr < kRows; ++rr) {
-            if (rr < nr) {
-              const float4 x = x4[rr * k4 + i];
-#pragma unroll
-              for (int o = 0; o < OUT; ++o) {
-                const float4 w = wreg[it][o];
-                float a = acc[o * kRows + rr];
-                a = fmaf(w.x, x.x, a); a = fmaf(w.y, x.y, a); a = fmaf(w.z, x.z, a); a = fmaf(w.w, x.w, a);
-                acc[o * kRows + rr] = a;
+                for (int r = 0; r < kRG; ++r) {
+                  float a = acc[r * kOB + o];
+                  a = fmaf(w.x, x[r][j].x, a); a = fmaf(w.y, x[r][j].y, a);
+                  a = fmaf(w.z, x[r][j].z, a); a = fmaf(w.w, x[r][j].w, a);
+                  acc[r * kOB + o] = a;
+                }
               }
             }
           }
         }
       }
-      // warp totals: lane l <- total of partial l (and l + 32 when there are 64)
-      float t0, t1 = 0.f;
-      if (OUT * kRows == 64) {
-        float lo[32], hi[32];
+      const float tot = warp_transpose_reduce(acc);     // lane l: total of partial l = (row l / kOB, output l % kOB)
+      if (e_ok) {
+        const int o = o_lo + evo / taps;
+        int row = rid[0];
 #pragma unroll
-        for (int q = 0; q < 32; ++q) { lo[q] = acc[q]; hi[q] = acc[q + 32]; }
-        t0 = warp_transpose_reduce(lo);
-        t1 = warp_transpose_reduce(hi);
-      } else {
-        float lo[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) lo[q] = acc[q];
-        t0 = warp_transpose_reduce(lo);
-      }
-      partial[warp * 64 + lane] = t0;
-      if (OUT * kRows == 64) partial[warp * 64 + 32 + lane] = t1;
-      __syncthreads();
-      if (tid < OUT * kRows) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v += partial[w * 64 + tid];
-        const int o = tid / kRows, rr = tid % kRows;
-        if (rr < nr && o0 + o < nout) {
-          v += bias ? __ldg(bias + o0 + o) : 0.f;
+        for (int r = 1; r < kRG; ++r) row = (er == r) ? rid[r] : row;
+        if (epi.mode == 0) {
+          float v = tot + (bias ? __ldg(bias + o) : 0.f);
           if (GELU) v = gelu_erf(v);
-          out[rows[r0 + rr] * out_stride + o0 + o] = v;
+          out[row * out_stride + o] = v;
+        } else if (evo % taps == taps - 1) {                     // newest tap: position n is complete
+          float v = prev + tot + __ldg(bias + o);
+          if (GELU) v = gelu_erf(v);
+          out[row * out_stride + o] = v;
+          *slot = 0.f;                                           // the slot next collects position n + taps
+        } else {
+          *slot = prev + tot;
         }
       }
-      // the next iteration's first __syncthreads (after its cp.async wait) orders these reads before partial is rewritten
-      __syncthreads();
     }
   }
 }
 
+// Grid-wide barrier: cooperative_groups' grid.sync().  Measured on 148 CTAs x 256 threads (scripts/barrier_probe.cu):
+// grid.sync 1.21 us, one-counter atomicAdd + acquire spin 1.34 us, 16 spread counters + top counter 1.76 us, per-CTA
+// flags gathered by CTA 0 2.02 us -- so the library primitive stays.  (Its fences also drop the SM's L1 lines.)
+__device__ __forceinline__ void grid_barrier(unsigned*, unsigned&) { cg::this_grid().sync(); }
+
+// per-thread (best, second, index) -> block-wide argmax with lowest index on ties; result in s_*[0]
+__device__ __forceinline__ void block_argmax(float best, float second, int idx, float* s_best, float* s_second, int* s_idx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto merge = [&](float b2, float s2, int i2) {
+    if (b2 > best || (b2 == best && i2 < idx)) { second = fmaxf(best, s2); best = b2; idx = i2; }
+    else second = fmaxf(second, b2);
+  };
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, o), s2 = __shfl_xor_sync(0xffffffffu, second, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    merge(b2, s2, i2);
+  }
+  __syncthreads();
+  if (lane == 0) { s_best[warp] = best; s_second[warp] = second; s_idx[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    const bool have = lane < kThreads / 32;
+    best = have ? s_best[lane] : -INFINITY; second = have ? s_second[lane] : -INFINITY; idx = have ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float b2 = __shfl_xor_sync(0xffffffffu, best, o), s2 = __shfl_xor_sync(0xffffffffu, second, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+      merge(b2, s2, i2);
+    }
+    if (lane == 0) { s_best[0] = best; s_second[0] = second; s_idx[0] = idx; }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p) {
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[kThreads / 32];
-  __shared__ float partial[(kThreads / 32) * 64];
-  __shared__ float s_best[kThreads];
-  __shared__ float s_second[kThreads];
-  __shared__ int s_idx[kThreads];
+  __shared__ float s_best[kThreads / 32];
+  __shared__ float s_second[kThreads / 32];
+  __shared__ int s_idx[kThreads / 32];
   const int B = p.B, H = p.H, V = p.V, E = p.E;
   const int tid = threadIdx.x;
+  const int G = gridDim.x, cta = blockIdx.x;
   int* rows_act = p.rows;          // compacted list of active utterances (P2) ...
   int* rows_emit = p.rows + B;     // ... and of utterances that emitted in this step (P4-P6)
   int* counts = p.flags;           // [0] n_active, [1] n_emit, [2] n_active_next
-  const bool timer = (blockIdx.x == 0 && tid == 0 && p.prof != nullptr);
+  unsigned* bar_counter = p.bar;   // zeroed by the launcher
+  unsigned bar_target = 0;         // number of barriers passed so far
+  const bool timer = (cta == 0 && tid == 0 && p.prof != nullptr);
   long long tmark = timer ? clock64() : 0;
   auto lap = [&](int slot) { if (timer) { const long long now = clock64(); p.prof[slot] += now - tmark; tmark = now; } };
   if (timer) for (int i = 0; i < 8; ++i) p.prof[i] = 0;
 
-  // ---- init: state, seed token = blank for every utterance, everyone "emits" the seed so the predictor runs once
-  for (int i = blockIdx.x * kThreads + tid; i < B * 2 * E; i += gridDim.x * kThreads) p.xs[i] = 0.f;
-  for (int i = blockIdx.x * kThreads + tid; i < B * 4 * E; i += gridDim.x * kThreads) p.ys[i] = 0.f;
-  if (blockIdx.x == 0) {
+  // ---- this CTA's output slices of the four weight matrices; resident in shared memory where the launcher found room
+  const int perJ = (V + G - 1) / G, perE = (E + G - 1) / G, perL = (H + G - 1) / G;
+  const int j_lo = min(V, cta * perJ), j_hi = min(V, j_lo + perJ);
+  const int e_lo = min(E, cta * perE), e_hi = min(E, e_lo + perE);
+  const int l_lo = min(H, cta * perL), l_hi = min(H, l_lo + perL);
+  const float* Wj_s = p.Wj + static_cast<long long>(j_lo) * H;
+  const float* w1_s = p.w1 + static_cast<long long>(e_lo) * 3 * E;
+  const float* w2_s = p.w2 + static_cast<long long>(e_lo) * 5 * E;
+  const float* wl_s = p.wl + static_cast<long long>(l_lo) * E;
+  float* xstage = nullptr;     // per-warp activation staging buffers, after the resident weight slices
+  {
+    // fixed offsets (every CTA reserves per* rows, so the residency decision is the launcher's alone)
+    const long long off_j = 0;
+    const long long off_2 = off_j + ((p.resident & 1) ? static_cast<long long>(perJ) * H : 0);
+    const long long off_1 = off_2 + ((p.resident & 2) ? static_cast<long long>(perE) * 5 * E : 0);
+    const long long off_l = off_1 + ((p.resident & 4) ? static_cast<long long>(perE) * 3 * E : 0);
+    auto stage = [&](const float*& w, int nrows, int K, bool resident, long long off) {
+      if (!resident) return;
+      const float4* src = reinterpret_cast<const float4*>(w);
+      float4* d4 = reinterpret_cast<float4*>(smem + off);
+      for (int i = tid; i < nrows * (K >> 2); i += kThreads) d4[i] = __ldg(src + i);
+      w = smem + off;
+    };
+    xstage = smem + p.weight_floats;
+    stage(Wj_s, j_hi - j_lo, H, p.resident & 1, off_j);
+    stage(w2_s, e_hi - e_lo, 5 * E, p.resident & 2, off_2);
+    stage(w1_s, e_hi - e_lo, 3 * E, p.resident & 4, off_1);
+    stage(wl_s, l_hi - l_lo, E, p.resident & 8, off_l);
+  }
+
+  // ---- init: conv tap accumulators = 0 (left zero padding), LayerNorm(embedding) table for every symbol, seed token =
+  // blank for every utterance, everyone "emits" the seed so the predictor runs once
+  for (int i = cta * kThreads + tid; i < B * 3 * E; i += G * kThreads) p.acc1[i] = 0.f;
+  for (int i = cta * kThreads + tid; i < B * 5 * E; i += G * kThreads) p.acc2[i] = 0.f;
+  if (cta == 0) {
     for (int b = tid; b < B; b += kThreads) {
-      p.t_idx[b] = 0; p.per[b] = 0; p.ntok[b] = 1; p.emit[b] = 1; rows_emit[b] = b;
+      p.t_idx[b] = 0; p.per[b] = 0; p.ntok[b] = 1; p.emit[b] = 1; rows_emit[b] = b; p.last_tok[b] = p.blank;
     }
     if (tid == 0) { counts[0] = 0; counts[1] = B; counts[2] = 0; }
   }
-  for (int b = blockIdx.x; b < B; b += gridDim.x)
-    block_layer_norm(p.emb + static_cast<long long>(p.blank) * E, p.ln1_w, p.ln1_b, p.xnew + b * E, E, red);
-  grid.sync();
+  for (int v = cta; v < p.NS; v += G)
+    block_layer_norm(p.emb + static_cast<long long>(v) * E, p.ln1_w, p.ln1_b, p.emb_ln + static_cast<long long>(v) * E, E, red);
+  grid_barrier(bar_counter, bar_target);
 
   for (int step = 0;; ++step) {
-    const int n_emit = counts[1];
+    const int n_emit = __ldcg(counts + 1);
     if (n_emit > 0) {
-      // ---- P4: conv1 at the new position: [xs(b,0), xs(b,1), xnew(b)] . w1^T
+      // ---- P4: conv1, tap products of the new symbol's layer-normed embedding (row last_tok[b] of the table)
       {
-        Seg segs[2] = {{p.xs, 2LL * E, 2 * E}, {p.xnew, E, E}};
-        batched_gemv<true, 8>(p.w1, p.b1, E, 3 * E, segs, 2, rows_emit, n_emit, p.ynew, E, smem, p.smem_floats, partial, p.rsplit_e);
+        GemvEpi epi{1, 3, p.acc1, p.ntok, E};
+        gemv_phase<true>(w1_s, p.b1, e_lo, e_hi, E, 3 * E, p.emb_ln, E, p.last_tok, rows_emit, n_emit, p.ynew, E, epi, xstage);
       }
       lap(3);
-      grid.sync();
+      grid_barrier(bar_counter, bar_target);
       lap(7);
-      // ---- P5: conv2 at the new position: [ys(b,0..3), ynew(b)] . w2^T ; conv1 state shifts (xs is no longer read)
+      // ---- P5: conv2, tap products of the new conv1 output
       {
-        Seg segs[2] = {{p.ys, 4LL * E, 4 * E}, {p.ynew, E, E}};
-        batched_gemv<true, 8>(p.w2, p.b2, E, 5 * E, segs, 2, rows_emit, n_emit, p.z, E, smem, p.smem_floats, partial, p.rsplit_e);
-      }
-      for (int j = blockIdx.x; j < n_emit; j += gridDim.x) {
-        const int b = rows_emit[j];
-        for (int i = tid; i < E; i += kThreads) {
-          p.xs[(b * 2 + 0) * E + i] = p.xs[(b * 2 + 1) * E + i];
-          p.xs[(b * 2 + 1) * E + i] = p.xnew[b * E + i];
-        }
+        GemvEpi epi{1, 5, p.acc2, p.ntok, E};
+        gemv_phase<true>(w2_s, p.b2, e_lo, e_hi, E, 5 * E, p.ynew, E, nullptr, rows_emit, n_emit, p.z, E, epi, xstage);
       }
       lap(4);
-      grid.sync();
+      grid_barrier(bar_counter, bar_target);
       lap(7);
-      // ---- P6: linear ; conv2 state shifts (ys is no longer read)
+      // ---- P6: linear
       {
-        Seg segs[1] = {{p.z, E, E}};
-        batched_gemv<false, 8>(p.wl, p.bl, H, E, segs, 1, rows_emit, n_emit, p.lin, H, smem, p.smem_floats, partial);
-      }
-      for (int j = blockIdx.x; j < n_emit; j += gridDim.x) {
-        const int b = rows_emit[j];
-        for (int i = tid; i < E; i += kThreads) {
-          const float y0 = p.ys[(b * 4 + 1) * E + i], y1 = p.ys[(b * 4 + 2) * E + i], y2 = p.ys[(b * 4 + 3) * E + i];
-          p.ys[(b * 4 + 0) * E + i] = y0;
-          p.ys[(b * 4 + 1) * E + i] = y1;
-          p.ys[(b * 4 + 2) * E + i] = y2;
-          p.ys[(b * 4 + 3) * E + i] = p.ynew[b * E + i];
-        }
+        GemvEpi epi{0, 1, nullptr, nullptr, E};
+        gemv_phase<false>(wl_s, p.bl, l_lo, l_hi, E, E, p.z, E, nullptr, rows_emit, n_emit, p.lin, H, epi, xstage);
       }
       lap(5);
-      grid.sync();
+      grid_barrier(bar_counter, bar_target);
       lap(7);
     }
     if (step >= p.max_steps) break;
 
     // ---- P1: refresh predictor features where a token was emitted; joint hidden rows for active utterances
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-      if (p.emit[b]) block_layer_norm(p.lin + static_cast<long long>(b) * H, p.ln2_w, p.ln2_b, p.feats + static_cast<long long>(b) * H, H, red);
+    for (int b = cta; b < B; b += G) {
+      if (__ldcg(p.emit + b)) block_layer_norm(p.lin + static_cast<long long>(b) * H, p.ln2_w, p.ln2_b, p.feats + static_cast<long long>(b) * H, H, red);
       __syncthreads();
-      const int t = p.t_idx[b];
-      const bool active = t < p.T_len[b] && p.ntok[b] < p.max_len;
+      const int t = __ldcg(p.t_idx + b);
+      const bool active = t < p.T_len[b] && __ldcg(p.ntok + b) < p.max_len;
       if (active) {
         const float* e = p.enc + b * p.enc_sb + static_cast<long long>(t) * p.enc_st;
-        for (int i = tid; i < H; i += kThreads) p.hbuf[static_cast<long long>(b) * H + i] = tanhf(e[i] + p.feats[static_cast<long long>(b) * H + i]);
+        for (int i = tid; i < H; i += kThreads) p.hbuf[static_cast<long long>(b) * H + i] = tanhf(__ldg(e + i) + p.feats[static_cast<long long>(b) * H + i]);
       }
     }
-    if (blockIdx.x == 0) {
-      // compact the active list (single warp, order preserved)
+    if (cta == G - 1) {
+      // compact the active list (single warp, order preserved); the last CTA has no utterance of its own when B < G
       if (tid < 32) {
         int n = 0;
         for (int b0 = 0; b0 < B; b0 += 32) {
           const int b = b0 + tid;
-          const bool a = b < B && p.t_idx[b] < p.T_len[b] && p.ntok[b] < p.max_len;
+          const bool a = b < B && __ldcg(p.t_idx + b) < p.T_len[b] && __ldcg(p.ntok + b) < p.max_len;
           const unsigned m = __ballot_sync(0xffffffffu, a);
           if (a) rows_act[n + __popc(m & ((1u << tid) - 1))] = b;
           n += __popc(m);
@@ -323,66 +383,53 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
       }
     }
     lap(0);
-    grid.sync();
+    grid_barrier(bar_counter, bar_target);
     lap(7);
-    const int n_act = counts[0];
+    const int n_act = __ldcg(counts + 0);
     if (n_act == 0) break;
+    if (timer) p.prof[6] += 1;      // joint steps taken (slot 6 of the phase counters)
 
     // ---- P2: joint logits for the active rows
     {
-      Seg segs[1] = {{p.hbuf, H, H}};
-      batched_gemv<false, 8>(p.Wj, p.bj, V, H, segs, 1, rows_act, n_act, p.logits, V, smem, p.smem_floats, partial);
+      GemvEpi epi{0, 1, nullptr, nullptr, E};
+      gemv_phase<false>(Wj_s, p.bj, j_lo, j_hi, H, H, p.hbuf, H, nullptr, rows_act, n_act, p.logits, V, epi, xstage);
     }
     lap(1);
-    grid.sync();
+    grid_barrier(bar_counter, bar_target);
     lap(7);
 
     // ---- P3: argmax + decode rule + embedding layer norm, one CTA per active utterance
-    for (int j = blockIdx.x; j < n_act; j += gridDim.x) {
-      const int b = rows_act[j];
+    for (int j = cta; j < n_act; j += G) {
+      const int b = __ldcg(rows_act + j);
       const float* row = p.logits + static_cast<long long>(b) * V;
       float best = -INFINITY, second = -INFINITY;
       int idx = 0x7fffffff;
       for (int v = tid; v < V; v += kThreads) {
-        const float x = row[v];
+        const float x = __ldcg(row + v);
         if (x > best) { second = best; best = x; idx = v; }
         else if (x > second) second = x;
       }
-      __syncthreads();
-      s_best[tid] = best; s_second[tid] = second; s_idx[tid] = idx;
-      __syncthreads();
-      for (int o = kThreads >> 1; o; o >>= 1) {
-        if (tid < o) {
-          const float b2 = s_best[tid + o], s2 = s_second[tid + o];
-          const int i2 = s_idx[tid + o];
-          float b1 = s_best[tid], s1 = s_second[tid];
-          int i1 = s_idx[tid];
-          if (b2 > b1 || (b2 == b1 && i2 < i1)) { s1 = fmaxf(b1, s2); b1 = b2; i1 = i2; }
-          else s1 = fmaxf(s1, b2);
-          s_best[tid] = b1; s_second[tid] = s1; s_idx[tid] = i1;
-        }
-        __syncthreads();
-      }
+      block_argmax(best, second, idx, s_best, s_second, s_idx);
       // torch.argmax always returns an in-range index; a row without any finite maximum (all NaN / -inf) maps to 0
       const int tok = static_cast<unsigned>(s_idx[0]) < static_cast<unsigned>(V) ? s_idx[0] : 0;
-      const bool advance = (tok == p.blank) || (p.per[b] >= p.max_per_frame);
+      const bool advance = (tok == p.blank) || (__ldcg(p.per + b) >= p.max_per_frame);
       __syncthreads();
       if (tid == 0) {
         if (p.margins) p.margins[static_cast<long long>(step) * B + b] = s_best[0] - s_second[0];
         if (advance) {
-          p.t_idx[b] += 1; p.per[b] = 0; p.emit[b] = 0;
+          p.t_idx[b] = __ldcg(p.t_idx + b) + 1; p.per[b] = 0; p.emit[b] = 0;
         } else {
-          p.tokens[static_cast<long long>(b) * p.max_len + p.ntok[b] - 1] = tok;
-          p.ntok[b] += 1; p.per[b] += 1; p.emit[b] = 1;
+          const int nt = __ldcg(p.ntok + b);
+          p.tokens[static_cast<long long>(b) * p.max_len + nt - 1] = tok;
+          p.ntok[b] = nt + 1; p.per[b] = __ldcg(p.per + b) + 1; p.emit[b] = 1; p.last_tok[b] = tok;
           rows_emit[atomicAdd(&counts[1], 1)] = b;
         }
       }
-      if (!advance) block_layer_norm(p.emb + static_cast<long long>(tok) * E, p.ln1_w, p.ln1_b, p.xnew + b * E, E, red);
       __syncthreads();
     }
     // (a finished utterance may keep emit = 1; P1 then recomputes the same feats from an unchanged lin -- harmless)
     lap(2);
-    grid.sync();
+    grid_barrier(bar_counter, bar_target);
     lap(7);
   }
 }
@@ -393,55 +440,66 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
 // starts 16-byte aligned whatever B, V, E are (cp.async / float4 need it) | int regions].
 namespace {
 inline size_t pad4(size_t n) { return (n + 3) & ~static_cast<size_t>(3); }
-constexpr size_t kTimerBytes = 64;
+constexpr size_t kTimerBytes = 128;
+constexpr size_t kBarBytes = 128;      // reserved (a counter line for a hand-rolled grid barrier; grid.sync is used)
 }  // namespace
 
 size_t greedy_decode_scratch_bytes(int B, int H, int V, int E) {
   const size_t b = static_cast<size_t>(B);
-  const size_t floats = 3 * pad4(b * H) /*feats, hbuf, lin*/ + pad4(b * V) /*logits*/ + pad4(b * 2 * E) + pad4(b * 4 * E) +
-                        3 * pad4(b * E) /*xnew, ynew, z*/;
-  const size_t ints = b * 5 + 16;
-  return kTimerBytes + floats * 4 + ints * 4 + 256;
+  const size_t floats = 3 * pad4(b * H) /*feats, hbuf, lin*/ + pad4(b * V) /*logits*/ + pad4(b * 3 * E) + pad4(b * 5 * E) +
+                        2 * pad4(b * E) /*ynew, z*/ + pad4(static_cast<size_t>(V) * E) /*LayerNorm(embedding) table*/;
+  const size_t ints = b * 6 + 16;
+  return kTimerBytes + kBarBytes + floats * 4 + ints * 4 + 256;
 }
 
 int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream) {
   ProfScope prof_(kProfOther, stream);
   RB_REQUIRE(a.B > 0 && a.H > 0 && a.V > 1 && a.E > 0 && a.max_len >= 1, -1, "invalid decode shape");
-  const int klen_max = std::max(std::max(a.H, 5 * a.E), 3 * a.E);
-  const size_t smem_min = 2 * static_cast<size_t>(kRows) * klen_max * sizeof(float);   // at least double-buffered staging
-  const size_t smem = std::max<size_t>(smem_min, 192 * 1024);   // deeper ring (up to 4 chunks) for the narrower phases
-  a.smem_floats = static_cast<int>(smem / sizeof(float));
-  // conv phases: E/8 output blocks x rsplit row ranges should just fill the grid (E=512: 64 x 2 = 128 tasks on 148 SMs)
-  a.rsplit_e = std::max(1, std::min(4, device_sm_count() / std::max(1, (a.E + 7) / 8)));
-  RB_REQUIRE(smem <= 200 * 1024 && klen_max <= 4 * kMaxIt * kThreads, -6,
-             "decode kernel supports hidden_features <= 3072 and embedding dim <= 614");
+  RB_REQUIRE(a.H % 4 == 0 && a.E % 4 == 0, -2, "decode kernel needs hidden / embedding sizes that are multiples of 4");
+  const int grid = device_sm_count();
+  // Weight residency: each CTA keeps its output slice of a matrix in shared memory if it fits the budget, in the order
+  // joint (read every step), conv2, conv1, linear; whatever does not fit is streamed from L2 every step instead.
+  const size_t xstage_bytes = static_cast<size_t>(kThreads / 32) * kRG * 32 * kJ * sizeof(float4);   // 64 KB
+  const size_t budget = 220 * 1024 - xstage_bytes;
+  auto per = [&](int n) { return static_cast<size_t>((n + grid - 1) / grid); };
+  const size_t need[4] = {per(a.V) * a.H * 4, per(a.E) * 5 * a.E * 4, per(a.E) * 3 * a.E * 4, per(a.H) * a.E * 4};
+  size_t smem = 0;
+  a.resident = 0;
+  for (int i = 0; i < 4; ++i)
+    if (smem + need[i] <= budget) { smem += need[i]; a.resident |= 1 << i; }
+  a.weight_floats = static_cast<int>(smem / sizeof(float));
+  smem += xstage_bytes;
   // carve the scratch
   RB_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, -3, "decode scratch must be 16-byte aligned");
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 127) == 0, -3, "decode scratch must be 128-byte aligned");
   a.prof = reinterpret_cast<long long*>(scratch);          // 8 x int64 at the (aligned) start
-  float* f = scratch + kTimerBytes / sizeof(float);
+  a.bar = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + kTimerBytes);
+  RB_CUDA_CHECK(cudaMemsetAsync(a.bar, 0, kBarBytes, stream));
+  float* f = scratch + (kTimerBytes + kBarBytes) / sizeof(float);
   const int B = a.B, H = a.H, V = a.V, E = a.E;
   const size_t b = static_cast<size_t>(B);
   a.feats = f; f += pad4(b * H);
   a.hbuf = f; f += pad4(b * H);
   a.logits = f; f += pad4(b * V);
-  a.xs = f; f += pad4(b * 2 * E);
-  a.ys = f; f += pad4(b * 4 * E);
-  a.xnew = f; f += pad4(b * E);
+  a.acc1 = f; f += pad4(b * 3 * E);
+  a.acc2 = f; f += pad4(b * 5 * E);
   a.ynew = f; f += pad4(b * E);
   a.z = f; f += pad4(b * E);
   a.lin = f; f += pad4(b * H);
+  a.emb_ln = f; f += pad4(static_cast<size_t>(a.NS) * E);
   int* ip = reinterpret_cast<int*>(f);
   a.t_idx = ip; ip += B;
   a.per = ip; ip += B;
   a.emit = ip; ip += B;
   a.rows = ip; ip += 2 * B;
+  a.last_tok = ip; ip += B;
   a.flags = ip; ip += 16;
   RB_CUDA_CHECK(cudaFuncSetAttribute(greedy_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   RB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_decode_kernel, kThreads, smem));
   RB_REQUIRE(per_sm >= 1, -6, "decode kernel does not fit on an SM");
-  const int grid = device_sm_count();
   void* args[] = {&a};
+  // cooperative launch: guarantees that all CTAs are co-resident, which the kernel's own grid barrier relies on
   RB_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(greedy_decode_kernel), dim3(grid), dim3(kThreads),
                                             args, smem, stream));
   return 0;

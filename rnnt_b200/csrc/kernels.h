@@ -87,12 +87,16 @@ struct DecodeArgs {
   const float* w2; const float* b2;                       // conv2 as (E, 5E)
   const float* wl; const float* bl;                       // linear (H,E), (H)
   const float* ln2_w; const float* ln2_b;                 // output LayerNorm (H)
-  int B, T, H, V, E, blank, max_len, max_per_frame, max_steps, smem_floats, rsplit_e;
+  int B, T, H, V, E, blank, max_len, max_per_frame, max_steps;
+  int weight_floats;       // floats of dynamic shared memory taken by the resident weight slices (staging follows)
+  int resident;            // bit i: weight matrix i (joint, conv2, conv1, linear) has its per-CTA slice in shared memory
   int* tokens;             // (B, max_len) emitted tokens (seed blank excluded)
   int* ntok;               // (B) 1 + number of emitted tokens
   // scratch (carved by the launcher)
-  float *feats, *hbuf, *logits, *xs, *ys, *xnew, *ynew, *z, *lin, *margins;
-  int *t_idx, *per, *emit, *rows, *flags;
+  float *feats, *hbuf, *logits, *acc1, *acc2, *ynew, *z, *lin, *emb_ln, *margins;
+  int *t_idx, *per, *emit, *rows, *last_tok, *flags;
+  unsigned* bar;           // grid-barrier counters (one per 128-byte line)
+  int NS;                  // number of symbols = rows of the embedding table
   long long* prof;         // 8 cycle counters (block 0): P1, P2, P3, P4, P5, P6, -, grid barriers
 };
 
