@@ -21,7 +21,8 @@ METRICS = [
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
-    "lts__t_bytes.sum", "launch__registers_per_thread", "launch__block_size", "launch__grid_size",
+    "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex.sum", "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "smsp__inst_executed_pipe_lsu.sum", "launch__registers_per_thread", "launch__block_size", "launch__grid_size",
     "launch__cluster_dim_x", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
 ]
 UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
@@ -80,7 +81,7 @@ def main():
         tot[k][0] += 1
         tot[k][1] += us
     total = sum(v[1] for v in tot.values())
-    lines = [f"# launch list summary: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
+    lines = [f"# launch list summary: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra --sustain-s 0",
              "# per-launch times are cold-cache and serialised; compare SHARES with bench.py's live CUDA-event shares",
              f"{'kernel':<66s}{'launches':>9s}{'total_us':>12s}{'share':>8s}"]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
