@@ -5,6 +5,7 @@ Utterances shard across ranks with no data-path collective; the only exchange is
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, Sequence
 
 import torch
@@ -54,6 +55,9 @@ class WeightGradBucket:
             self.event = torch.cuda.Event()
             self.event.record(torch.cuda.current_stream(self.device))   # materialises the cudaEvent_t handle
         self.pending = False
+        # "overlap": joint slice all-reduced as soon as dW/db are final (under the dh GEMM), the rest at finish();
+        # "single": one all-reduce of the whole bucket at finish() on the side stream; "inline": same on the compute stream
+        self.mode = os.environ.get("RNNT_B200_BUCKET_MODE", "overlap")
         self.time_collectives = False      # bench.py: bracket every collective with CUDA events on the side stream
         self._timing = []
         self._exposed = []
@@ -105,7 +109,7 @@ class WeightGradBucket:
 
     def weight_grads_enqueued(self):
         """Called right after the backward's kernels were enqueued: dW / db are final once `event` fires."""
-        if self._world() == 1:
+        if self._world() == 1 or self.mode != "overlap":
             return
         if self.stream is not None:
             self.stream.wait_event(self.event)
@@ -121,12 +125,18 @@ class WeightGradBucket:
         world = self._world()
         if world == 1:
             return self.flat
+        import contextlib
+        if self.mode == "inline" and self.stream is not None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                self.flat.div_(world)
+            self.pending = False
+            return self.flat
         cur = torch.cuda.current_stream(self.device) if self.stream is not None else None
         if self.stream is not None:
             self.stream.wait_stream(cur)
             ctx = torch.cuda.stream(self.stream)
         else:
-            import contextlib
             ctx = contextlib.nullcontext()
         with ctx:
             rest = self.extra_slice if self.pending else self.flat
