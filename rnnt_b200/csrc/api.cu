@@ -286,6 +286,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
     g.n_active = n_active; g.sub_list = sub_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
     g.slot_begin = slot_begin; g.slot_cap = static_cast<int>(ring_slots); g.dW = dW; g.db = dbias; g.gscale = gscale;
     g.dW_fx = fx_w; g.db_fx = fx_b;
+    if (getenv("RNNT_B200_NO_DB")) g.db = nullptr;   // diagnostics: what the db column sums cost inside the dW kernel
     rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_slots, stream);
     if (rc) return rc;
     if (c == nchunks - 1) {

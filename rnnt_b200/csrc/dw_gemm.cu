@@ -61,7 +61,7 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
   const int k_begin = static_cast<int>(static_cast<long long>(nkc) * ks / p.ksplit);
   const int k_end = static_cast<int>(static_cast<long long>(nkc) * (ks + 1) / p.ksplit);
   if (k_begin >= k_end) return;   // uniform over the pair
-  const bool do_db = (ht == 0);
+  const bool do_db = (ht == 0) && p.db != nullptr;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmGmn);
