@@ -27,7 +27,8 @@ struct SmemLayout {
   static constexpr int b_ring = 0;
   static constexpr int a_ring = b_ring + kStagesB * kBytesB;
   static constexpr int bars = a_ring + kStagesA * kBytesA;
-  static constexpr int total = bars + 256;
+  static constexpr int db_red = bars + 256;                  // 128 threads x 8 fp32 partial column sums
+  static constexpr int total = db_red + 128 * 8 * 4;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
@@ -154,29 +155,55 @@ dw_gemm_kernel(const __grid_constant__ CUtensorMap tmGmn, const __grid_constant_
     const int v = (vt * 2 + rank) * kTileM + row;
     const float inv_s = __ldg(p.gscale + 1);
     if (do_db) {
-      // column sums of g over the cells of every A stage (MN-major: 64 cell rows of 128 bytes per 64-v box)
-      const uint32_t col_off = (row >> 6) * 8192 + (row & 7) * 2;
-      const uint32_t chunk = (row & 63) >> 3;
-      float dsum = 0.f;
+      // Column sums of g over the cells of every A stage (MN-major: 64 cell rows of 128 bytes per 64-class box, 16-byte
+      // chunks XOR-swizzled by row & 7).  Thread = (16-byte chunk c of the 2 x 8 per row = 8 classes, row group rg): it
+      // reads rows rg, rg + 8, ... with one 16-byte load each and keeps 8 fp32 partial sums in registers for the whole
+      // kernel; the 8 row groups meet once at the end through shared memory.
+      const int et = threadIdx.x - 64;                      // 0 .. 127 over the four epilogue warps
+      const int c = et & 15, rg = et >> 4;
+      const uint32_t col_off = (c >> 3) * 8192;
+      float dacc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dacc[e] = 0.f;
       uint32_t ita = 0;
       for (int kc = k_begin; kc < k_end; ++kc, ++ita) {
         const uint32_t sa = ita % kStagesA, pha = (ita / kStagesA) & 1;
         mbar_wait(a_full + 8 * sa, pha);
         const uint32_t base = a_ring + sa * kBytesA + col_off;
-        float part = 0.f;
-#pragma unroll 16
-        for (int c = 0; c < kBK; ++c) {
-          uint16_t hbits;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hbits) : "r"(base + c * 128 + ((chunk ^ (c & 7)) << 4)));
-          part += __half2float(__ushort_as_half(hbits));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t r = rg + 8 * i;
+          uint32_t w0, w1, w2, w3;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                       : "r"(base + r * 128 + (((c & 7) ^ (r & 7)) << 4)));
+          const uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+            dacc[2 * q] += f.x;
+            dacc[2 * q + 1] += f.y;
+          }
         }
-        dsum += part;
         __syncwarp();
         if (lane == 0) mbar_arrive(a_empty + 8 * sa);
       }
-      if (v < p.V) {
-        if (p.db_fx) fx_add(p.db_fx + v, dsum);
-        else atomicAdd(p.db + v, dsum * inv_s);
+      float* red = reinterpret_cast<float*>(smem_gen + SmemLayout::db_red);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[(rg * 16 + c) * 8 + e] = dacc[e];
+      named_bar_sync(1, 128);
+      if (rg == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float t = 0.f;
+#pragma unroll
+          for (int g8 = 0; g8 < 8; ++g8) t += red[(g8 * 16 + c) * 8 + e];      // fixed order
+          const int vv = (vt * 2 + rank) * kTileM + (c >> 3) * 64 + (c & 7) * 8 + e;
+          if (vv < p.V) {
+            if (p.db_fx) fx_add(p.db_fx + vv, t);
+            else atomicAdd(p.db + vv, t * inv_s);
+          }
+        }
       }
     }
     mbar_wait(tmem_full, 0);
