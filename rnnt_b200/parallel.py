@@ -126,6 +126,9 @@ class WeightGradBucket:
         if world == 1:
             return self.flat
         import contextlib
+        if self.mode == "none":            # diagnostics only: no collective at all (what rank skew alone costs)
+            self.pending = False
+            return self.flat
         if self.mode == "inline" and self.stream is not None:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             if self.average:
