@@ -363,7 +363,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     const int sub = rg >> 2, tq = (rg & 3) * 4 + (rs >> 1) * 2, uq = (rs & 1) * 2;
     constexpr bool t_major = TMAJOR;
     const bool vec_ok = ((p.enc_sh | p.enc_sb) & 3) == 0;     // 16-byte aligned rows of the (B,H,T) tensor
-    const int wl = rg & 3, kk = lane >> 2, tq4 = lane & 3;    // T-major fetch: k rows 16 wl + kk (+8), frames 4 tq4 .. +3
+    const int wl = rg & 3, kk = lane >> 2, tq4 = lane & 3;    // T-major fetch: k rows 16 wl + 2 kk, + 1; frames 4 tq4 .. +3
     float* stage = reinterpret_cast<float*>(smem_gen + SL::enc_stage) + sub * (2 * kTileT * kBK);
     uint32_t cnt = 0, cc = 0;                                 // cc: running chunk counter = stage buffer parity
     RB_TILE_LOOP(cnt) {
@@ -405,7 +405,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         const int t = tc.t0 + 4 * tq4;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int k = kc * kBK + 16 * wl + kk + 8 * h;
+          const int k = kc * kBK + 16 * wl + 2 * kk + h;       // two ADJACENT k rows: their values pair up into 8-byte stores
           g[h] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (k < p.H) {
             const float* src = p.enc + tc.b * p.enc_sb + static_cast<long long>(k) * p.enc_sh;
@@ -420,14 +420,14 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           }
         }
       };
-      // stage[buf][t][k ^ ((t >> 2 & 3) << 3)]: writers (fixed frame offset, lanes = 8 k x 4 frame groups) and readers
-      // (fixed frame, 8 lanes x 8 consecutive k) both touch all 32 banks exactly once
+      // stage[buf][t][k ^ ((t >> 2 & 3) << 3)]: writers (fixed frame offset, lanes = 8 k pairs x 4 frame groups, one 8-byte
+      // store per frame) and readers (fixed frame, 8 lanes x 8 consecutive k, 16-byte loads) are both bank-conflict free
       auto stage_put = [&](uint32_t buf, const float4 (&g)[2]) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float* dst = stage + buf * (kTileT * kBK) + (4 * tq4) * kBK + ((16 * wl + kk + 8 * h) ^ (tq4 << 3));
-          dst[0] = g[h].x; dst[kBK] = g[h].y; dst[2 * kBK] = g[h].z; dst[3 * kBK] = g[h].w;
-        }
+        float2* dst = reinterpret_cast<float2*>(stage + buf * (kTileT * kBK) + (4 * tq4) * kBK + ((16 * wl + 2 * kk) ^ (tq4 << 3)));
+        dst[0] = make_float2(g[0].x, g[1].x);
+        dst[kBK / 2] = make_float2(g[0].y, g[1].y);
+        dst[kBK] = make_float2(g[0].z, g[1].z);
+        dst[3 * kBK / 2] = make_float2(g[0].w, g[1].w);
       };
       auto stage_get = [&](uint32_t buf, float4 (&e)[2][2]) {
 #pragma unroll
