@@ -120,7 +120,9 @@ int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const floa
  * oldest..newest (weight.permute(0,2,1).reshape(E,-1)); every other parameter is the module's tensor as is.
  * tokens (B, max_len) int32 receives the emitted tokens, n_tokens (B) = 1 + their count (the seed blank is counted,
  * as rnnt/model.py:53,64 does).  margins_out (optional, (T+max_len+2, B) fp32, caller-initialised) receives the top-2
- * logit gap at [step, b] for every step utterance b was active in.  scratch: rnnt_b200_greedy_decode_scratch_bytes. */
+ * logit gap at [step, b] for every step utterance b was active in.  scratch: rnnt_b200_greedy_decode_scratch_bytes
+ * bytes, 128-byte aligned; its first 64 bytes return eight int64 counters (cycles of phases P1..P6, joint steps taken,
+ * cycles in grid barriers) of CTA 0. */
 size_t rnnt_b200_greedy_decode_scratch_bytes(int B, int H, int V, int E);
 int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, const int32_t* T_len,
                             const float* joint_w, const float* joint_b, const float* emb, const float* ln1_w,

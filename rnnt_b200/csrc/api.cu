@@ -14,6 +14,23 @@ namespace {
 using rb::kTileM;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Diagnostic knobs (read once per process; none of them changes results except RNNT_B200_DBG / RNNT_B200_NO_DB, which
+// exist to measure what parts of a kernel cost):
+//   RNNT_B200_DBG      bit mask handed to the joint kernels (1 skip epilogue math, 2 skip producer math, 8 print grids, ...)
+//   RNNT_B200_NO_DB    leave db out of the dW kernel (db is then NOT computed)
+//   RNNT_B200_COMM_SMS SMs the last dh launch leaves idle when the caller passed a dw_done event (for a concurrent collective)
+struct EnvKnobs { int dbg; bool no_db; int comm_sms; };
+const EnvKnobs& env_knobs() {
+  static const EnvKnobs k = [] {
+    EnvKnobs e{};
+    const char* s = getenv("RNNT_B200_DBG");      e.dbg = s ? atoi(s) : 0;
+    e.no_db = getenv("RNNT_B200_NO_DB") != nullptr;
+    s = getenv("RNNT_B200_COMM_SMS");             e.comm_sms = s ? atoi(s) : 0;
+    return e;
+  }();
+  return k;
+}
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
 struct WsLayout {
@@ -166,7 +183,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
   a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
   a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
   a.slot_begin = 0; a.slot_cap = 0x3fffffff; a.sub_list = nullptr; a.n_active = nullptr;
-  { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
+  a.dbg = env_knobs().dbg;
   a.lp = lp; a.lse = lse; a.coef = nullptr; a.dcost = nullptr; a.gscale = nullptr; a.clamp = 0.f;
   a.h_out = hbuf; a.h_map = hidden ? 0 : 2; a.g_ring = nullptr;
   rc = rb::launch_joint_gemm(0, true, tmW, tmH, tmH2, a, 2 * max_tiles, stream);
@@ -276,7 +293,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
     a.T_len = T_len; a.U_len = U_len; a.tile_off = tile_off;
     a.B = B; a.T = T; a.U1 = U1; a.H = H; a.Hp = w.Hp; a.V = V; a.Vp = w.Vp; a.blank = blank;
     a.slot_begin = slot_begin; a.slot_cap = static_cast<int>(ring_slots); a.sub_list = sub_list; a.n_active = n_active;
-    { const char* e = getenv("RNNT_B200_DBG"); a.dbg = e ? atoi(e) : 0; }
+    a.dbg = env_knobs().dbg;
     a.lp = const_cast<float*>(lp); a.lse = nullptr; a.coef = coef; a.dcost = dcost; a.gscale = gscale; a.clamp = clamp;
     a.h_out = h_src; a.h_map = h_map; a.g_ring = g_ring;
     rc = rb::launch_joint_gemm(1, hidden == nullptr, tmW, tmHk, tmHk2, a, chunk_slots, stream);
@@ -286,7 +303,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
     g.n_active = n_active; g.sub_list = sub_list; g.h_map = h_map; g.tile_off = tile_off; g.B = B; g.H = H; g.Hp = w.Hp; g.V = V; g.Vp = w.Vp;
     g.slot_begin = slot_begin; g.slot_cap = static_cast<int>(ring_slots); g.dW = dW; g.db = dbias; g.gscale = gscale;
     g.dW_fx = fx_w; g.db_fx = fx_b;
-    if (getenv("RNNT_B200_NO_DB")) g.db = nullptr;   // diagnostics: what the db column sums cost inside the dW kernel
+    if (env_knobs().no_db) g.db = nullptr;
     rc = rb::launch_dw_gemm(tmGmn, tmHmn, g, chunk_slots, stream);
     if (rc) return rc;
     if (c == nchunks - 1) {
@@ -308,7 +325,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
     d.d_enc = d_enc; d.denc_sb = denc_sb; d.denc_st = denc_st; d.denc_sh = denc_sh; d.d_pred = d_pred;
     d.d_enc_fx = fx_enc; d.d_pred_fx = fx_pred;
     // with a dW-done event the caller is about to run a collective next to this kernel: leave it a few SMs
-    { const char* e = getenv("RNNT_B200_COMM_SMS"); d.spare_pairs = (dw_done_event && c == nchunks - 1) ? (e ? atoi(e) : 0) / 2 : 0; }
+    d.spare_pairs = (dw_done_event && c == nchunks - 1) ? env_knobs().comm_sms / 2 : 0;
     rc = rb::launch_dh_gemm(tmG128, tmWmn, d, chunk_slots, stream);
     if (rc) return rc;
   }
