@@ -94,6 +94,15 @@ __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, flo
   float* dptr = out + first;
   const int nb = BETA ? u + 1 : u - 1;                       // neighbour column feeding this one
   const bool last_col = u >= Ub;
+  // shared-memory addresses of the step, computed once: left to the compiler, every step re-derives them from
+  // SR_TID / SR_CgaCtaId (two special-register reads on the dependency chain of the wavefront)
+  uint32_t rd_addr[2] = {smem_u32(sh1 + nb), smem_u32(sh0 + nb)};          // step parity 0 reads sh1, writes sh0
+  uint32_t wr_addr[2] = {smem_u32(sh0 + u), smem_u32(sh1 + u)};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {      // opaque to the compiler, so that it keeps them in registers instead of rematerialising
+    asm volatile("mov.u32 %0, %0;" : "+r"(rd_addr[i]));
+    asm volatile("mov.u32 %0, %0;" : "+r"(wr_addr[i]));
+  }
 
   float2 cur[kPre], nxt[kPre];
   auto fetch = [&](int g, float2 (&d)[kPre]) {
@@ -117,12 +126,11 @@ __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, flo
     for (int i = 0; i < kPre; ++i) {
       const int s = g * kPre + i;
       if (s < ndiag) {    // uniform over the block
-        float* wr = (i & 1) ? sh1 : sh0;                     // kPre is even: the parity of s is the parity of i
-        const float* rd = (i & 1) ? sh0 : sh1;
-        float pub = -INFINITY;
+        float pub = -INFINITY;                               // (kPre is even: the parity of s is the parity of i)
         if (static_cast<unsigned>(s - s0) < static_cast<unsigned>(Tb)) {
           const float lpB = cur[i].x, lpE = cur[i].y;
-          const float side = rd[nb];                     // guards hold -inf at columns -1 and blockDim.x
+          float side;                                    // guards hold -inf at columns -1 and blockDim.x
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(side) : "r"(rd_addr[i & 1]) : "memory");
           if (!BETA) {
             const float val = lse2f(own, side);          // own = -inf at t = 0, side = -inf at u = 0
             own = val + lpB;                             // feeds alpha(t+1,u)
@@ -137,7 +145,7 @@ __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, flo
           }
           dptr += step;
         }
-        wr[u] = pub;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(wr_addr[i & 1]), "f"(pub) : "memory");
         __syncthreads();
       }
     }
