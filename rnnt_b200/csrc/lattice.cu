@@ -67,9 +67,9 @@ __global__ void convert_weights_kernel(const float* __restrict__ W, const float*
 // term bounded by ln 2) instead of the ~50-instruction expf/log1pf pair.
 __device__ __forceinline__ float lse2f(float a, float b) {
   const float m = fmaxf(a, b);
-  if (m == -INFINITY) return -INFINITY;
-  const float d = fminf(a, b) - m;                        // <= 0, may be -inf
-  return fmaf(lg2_approx(1.f + ex2_approx(d * kLog2e)), kLn2, m);
+  const float t = a - b;                                   // in parallel with the max; NaN only if both are -inf
+  const float r = fmaf(lg2_approx(1.f + ex2_approx(fabsf(t) * -kLog2e)), kLn2, m);   // one operand -inf: exp -> 0, r = m
+  return m == -INFINITY ? -INFINITY : r;
 }
 
 constexpr int kPre = 8;
@@ -126,25 +126,29 @@ __device__ __forceinline__ void lattice_walk(const float2* __restrict__ lp2, flo
     for (int i = 0; i < kPre; ++i) {
       const int s = g * kPre + i;
       if (s < ndiag) {    // uniform over the block
-        float pub = -INFINITY;                               // (kPre is even: the parity of s is the parity of i)
-        if (static_cast<unsigned>(s - s0) < static_cast<unsigned>(Tb)) {
-          const float lpB = cur[i].x, lpE = cur[i].y;
-          float side;                                    // guards hold -inf at columns -1 and blockDim.x
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(side) : "r"(rd_addr[i & 1]) : "memory");
-          if (!BETA) {
-            const float val = lse2f(own, side);          // own = -inf at t = 0, side = -inf at u = 0
-            own = val + lpB;                             // feeds alpha(t+1,u)
-            pub = val + lpE;                             // feeds alpha(t,u+1); -inf out of the last column
-            *dptr = val;
-          } else {
-            const float val = lse2f(own + lpB, side + lpE);   // own = -inf at t = Tb-1 except in the corner
-            own = val;
-            pub = val;
-            last = val;
-            *dptr = val;
-          }
-          dptr += step;
+        // (kPre is even: the parity of s is the parity of i.)  Every thread evaluates the step -- inactive ones on
+        // harmless operands -- and only the commit is predicated: no divergent branch on the wavefront's critical path.
+        const bool act = static_cast<unsigned>(s - s0) < static_cast<unsigned>(Tb);
+        const float lpB = cur[i].x, lpE = cur[i].y;
+        float side;                                          // guards hold -inf at columns -1 and blockDim.x
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(side) : "r"(rd_addr[i & 1]) : "memory");
+        float val, own_next, pub_next;
+        if (!BETA) {
+          val = lse2f(own, side);                            // own = -inf at t = 0, side = -inf at u = 0
+          own_next = val + lpB;                              // feeds alpha(t+1,u)
+          pub_next = val + lpE;                              // feeds alpha(t,u+1); -inf out of the last column
+        } else {
+          val = lse2f(own + lpB, side + lpE);                // own = -inf at t = Tb-1 except in the corner
+          own_next = val;
+          pub_next = val;
         }
+        if (act) {
+          *dptr = val;
+          dptr += step;
+          own = own_next;
+          if (BETA) last = val;
+        }
+        const float pub = act ? pub_next : -INFINITY;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(wr_addr[i & 1]), "f"(pub) : "memory");
         __syncthreads();
       }
