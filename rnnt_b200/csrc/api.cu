@@ -149,6 +149,7 @@ int rnnt_b200_joint_loss_fwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
   int rc = check_common(enc, enc_sb, enc_st, enc_sh, pred, B, T, U1, H, V, &blank);
   if (rc) return rc;
   const WsLayout w = ws_layout(B, T, U1, H, V, 0, hidden != nullptr);
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, -3, "W must be 16-byte aligned");
   RB_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 127) == 0, -3, "hidden must be 128-byte aligned");
   RB_REQUIRE(workspace != nullptr && workspace_bytes >= w.total_fwd, -7, "workspace too small: need %zu bytes",
              w.total_fwd);
@@ -204,6 +205,7 @@ int rnnt_b200_joint_loss_bwd(const float* enc, int64_t enc_sb, int64_t enc_st, i
   rc = check_layout("d_enc", denc_sb, denc_st, denc_sh, B, T, H);
   if (rc) return rc;
   RB_REQUIRE((reinterpret_cast<uintptr_t>(d_enc) & 15) == 0, -3, "d_enc must be 16-byte aligned");
+  RB_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, -3, "W must be 16-byte aligned");
   RB_REQUIRE((denc_sh == 1 && denc_st == H && denc_sb == static_cast<int64_t>(T) * H) ||
                  (denc_st == 1 && denc_sh == T && denc_sb == static_cast<int64_t>(T) * H),
              -3, "d_enc must be a dense (B,T,H) tensor or a dense (B,H,T) tensor viewed as (B,T,H)");

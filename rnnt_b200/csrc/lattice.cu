@@ -51,14 +51,22 @@ __global__ void tile_table_kernel(const int* __restrict__ T_len, const int* __re
   if (err_flag) *err_flag = bad;
 }
 
+// W (V,H) fp32 -> fp16 [Vp,Hp] zero-padded, 8 elements (one 16-byte store) per thread; bias * log2(e) with -1e30 padding.
 __global__ void convert_weights_kernel(const float* __restrict__ W, const float* __restrict__ bias, int V, int H,
                                        int Vp, int Hp, __half* __restrict__ Wh, float* __restrict__ bias2) {
-  const long long n = static_cast<long long>(Vp) * Hp;
+  const int hp8 = Hp >> 3;                                   // Hp is a multiple of 64, H a multiple of 8
+  const long long n = static_cast<long long>(Vp) * hp8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i / Hp), k = static_cast<int>(i % Hp);
-    const float x = (v < V && k < H) ? W[static_cast<long long>(v) * H + k] : 0.f;
-    Wh[i] = __float2half_rn(x);
+    const int v = static_cast<int>(i / hp8), k = static_cast<int>(i % hp8) * 8;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (v < V && k < H) {
+      const float4* src = reinterpret_cast<const float4*>(W + static_cast<long long>(v) * H + k);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      o.x = pack_f16x2(a.x, a.y); o.y = pack_f16x2(a.z, a.w);
+      o.z = pack_f16x2(b.x, b.y); o.w = pack_f16x2(b.z, b.w);
+    }
+    reinterpret_cast<uint4*>(Wh)[i] = o;
     if (k == 0) bias2[v] = (v < V) ? bias[v] * kLog2e : -1e30f;
   }
 }
@@ -374,7 +382,7 @@ int launch_tile_table(const int* T_len, const int* U_len, int B, int T, int U1, 
 int launch_convert_weights(const float* W, const float* bias, int V, int H, int Vp, int Hp, __half* Wh,
                            float* bias2, cudaStream_t stream) {
   ProfScope prof_(kProfPrep, stream);
-  const long long n = static_cast<long long>(Vp) * Hp;
+  const long long n = static_cast<long long>(Vp) * (Hp / 8);
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 4096));
   convert_weights_kernel<<<grid, 256, 0, stream>>>(W, bias, V, H, Vp, Hp, Wh, bias2);
   RB_CUDA_CHECK(cudaGetLastError());
