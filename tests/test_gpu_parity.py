@@ -893,3 +893,29 @@ def test_train_loop_guard_shapes_fit_in_bounded_memory():
         del loss, enc, W
     reference_need = 3 * B * T * (U + 1) * V * 4 / 2 ** 30      # logits + logit-gradients + fp32 activations (H = V)
     assert reference_need > 40 and peaks[True] < 12 and peaks[False] < 5, (reference_need, peaks)
+
+
+def test_fuzz_layouts_modes_and_chunking():
+    """Random small problems through random combinations of the code paths: encoder layout (dense / (B,H,T) view),
+    backward flags (all tiles, deterministic), saved or recomputed activations, single- or multi-chunk gradient ring."""
+    rng = np.random.default_rng(7)
+    for i in range(14):
+        B, T, U = int(rng.integers(1, 5)), int(rng.integers(1, 70)), int(rng.integers(0, 25))
+        H, V = int(rng.choice([8, 64, 72, 128, 256])), int(rng.choice([5, 64, 256, 300, 520]))
+        inp = make_inputs(B, T, U, H, V, ragged=True, seed=500 + i)
+        ref = torch_reference(inp, device="cpu")
+        view = bool(rng.integers(0, 2)) and T > 1
+        if view:
+            inp = dict(inp, enc=inp["enc"].permute(0, 2, 1).contiguous().permute(0, 2, 1))
+        flags = int(rng.integers(0, 4))
+        save_hidden = bool(rng.integers(0, 2))
+        ring = None if rng.integers(0, 2) else int(rng.integers(1, 6))
+        out = fused_raw(inp, flags=flags, save_hidden=save_hidden, ring_tiles=ring)
+        tag = (B, T, U, H, V, view, flags, save_hidden, ring)
+        assert out["status"] == 0, tag
+        err = (out["costs"].cpu() - ref["costs"]).abs()
+        assert (err <= LOSS_RTOL * ref["costs"].abs() + 3e-4).all(), (tag, out["costs"], ref["costs"])
+        tol = GRAD_TOL_TINY if H < 64 else GRAD_TOL_FP32
+        for k in ("d_enc", "d_pred", "dW", "db"):
+            r, a = rel_err(out[k].cpu(), ref[k])
+            assert r <= tol or a < 1e-5, (tag, k, r, a)
