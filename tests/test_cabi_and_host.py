@@ -43,6 +43,25 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert n == len(_lib._SIGNATURES[name][1]), (name, n, len(_lib._SIGNATURES[name][1]))
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/rnnt_b200.h is the drop-in boundary: it must compile as C99 with nothing but <stddef.h> / <stdint.h>, and a
+    C translation unit that takes the address of every declared entry point must link against the library."""
+    syms = _header_symbols()
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "rnnt_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void* fns[] = {\n'
+                   + "".join(f"    (const void*)&{s},\n" for s in syms)
+                   + '  };\n  printf("%d %d\\n", (int)(sizeof(fns) / sizeof(fns[0])), rnnt_b200_abi_version());\n  return 0;\n}\n')
+    from rnnt_b200.build import LIB_PATH, build_extension
+    build_extension()
+    exe = tmp_path / "abi_check"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", os.path.dirname(LIB_PATH), "-lrnnt_b200", "-Wl,-rpath," + os.path.dirname(LIB_PATH)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == [str(len(syms)), "3"], (r.stdout, r.stderr)
+
+
 def test_argument_validation_without_gpu():
     from rnnt_b200 import _lib
     L = _lib.lib()
