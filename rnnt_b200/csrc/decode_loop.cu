@@ -14,8 +14,11 @@
 //   P1  feats = LayerNorm(lin) for utterances that just emitted; h = tanh(enc[b, t_b] + feats[b])
 //   P2  logits[b, v] = W_j[v,:] . h[b,:] + b_j[v]        (CTA = its ~V/148 classes, warp = 4 rows, lanes split K; gemv_phase)
 //   P3  argmax (lowest index on ties) + top-2 margin, blank / max-per-frame rule, token append
-//   P4  y = gelu(conv1) from the tap products of x = LN(emb[tok]) (table)   P5  z = gelu(conv2) likewise   P6  lin = linear(z)
-// P4-P6 only run in steps where some utterance emitted.  Every dot product is accumulated in a fixed order (thread-
+//       conv1 of an emitted token, inside P3: its tap products W1_j . LN(emb[tok]) depend on the token alone, so they are a
+//       (symbols, 3E) TABLE built once at kernel start (1.6 GFLOP, ~3 decode steps' worth) -- the step adds three table
+//       rows to the utterance's tap accumulators and applies bias + GELU: no GEMV phase, no grid barrier for conv1
+//   P5  z = gelu(conv2) from the tap products of the new conv1 output   P6  lin = linear(z)
+// P5-P6 only run in steps where some utterance emitted.  Every dot product is accumulated in a fixed order (thread-
 // strided partial sums, then one fixed warp butterfly), so results are deterministic.
 #include <cooperative_groups.h>
 
@@ -52,17 +55,45 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return red[0];
 }
 
-// dst[i] = LayerNorm(src)[i] * w[i] + b[i] over n elements, by the whole CTA (torch: biased variance, eps 1e-5)
+// dst[i] = LayerNorm(src)[i] * w[i] + b[i] over n elements, by the whole CTA (torch: biased variance, eps 1e-5).
+// The row is read ONCE (L2 round trip) into registers when it has at most kLnRegs elements per thread; the sums run in
+// the same thread-strided order either way.  `src` may have been written by other CTAs in this kernel: L2 loads only.
+constexpr int kLnRegs = 8;
 __device__ void block_layer_norm(const float* __restrict__ src, const float* __restrict__ w,
                                  const float* __restrict__ b, float* __restrict__ dst, int n, float* red) {
+  const bool cached = n <= kLnRegs * kThreads;
+  float x[kLnRegs];
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += kThreads) s += src[i];
+  if (cached) {
+#pragma unroll
+    for (int q = 0; q < kLnRegs; ++q) {
+      const int i = threadIdx.x + q * kThreads;
+      x[q] = i < n ? __ldcg(src + i) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kLnRegs; ++q) if (threadIdx.x + q * kThreads < n) s += x[q];
+  } else {
+    for (int i = threadIdx.x; i < n; i += kThreads) s += __ldcg(src + i);
+  }
   const float mean = block_sum(s, red) / n;
-  float q = 0.f;
-  for (int i = threadIdx.x; i < n; i += kThreads) { const float d = src[i] - mean; q += d * d; }
-  const float var = block_sum(q, red) / n;
+  float q2 = 0.f;
+  if (cached) {
+#pragma unroll
+    for (int q = 0; q < kLnRegs; ++q) if (threadIdx.x + q * kThreads < n) { const float d = x[q] - mean; q2 += d * d; }
+  } else {
+    for (int i = threadIdx.x; i < n; i += kThreads) { const float d = __ldcg(src + i) - mean; q2 += d * d; }
+  }
+  const float var = block_sum(q2, red) / n;
   const float rstd = rsqrtf(var + 1e-5f);
-  for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = (src[i] - mean) * rstd * w[i] + b[i];
+  if (cached) {
+#pragma unroll
+    for (int q = 0; q < kLnRegs; ++q) {
+      const int i = threadIdx.x + q * kThreads;
+      if (i < n) dst[i] = (x[q] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += kThreads) dst[i] = (__ldcg(src + i) - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+  }
 }
 
 __device__ __forceinline__ void cp_async16(float4* smem_dst, const float4* gsrc) {
@@ -109,8 +140,9 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32]) {
 //        ring acc[row][taps][E] (zero-initialised = the left zero padding of rnnt/causalconv.py:29).  The newest tap
 //        completes position n: out[row][o] = gelu(bias[o] + acc[row][n % taps][o] + dot) and the slot is cleared for
 //        position n + taps.  A step therefore reads E instead of taps*E activations per utterance.
+// EPI 2: the tap products themselves, no accumulation: out[row][j * E + o] = dot (the conv1 table: rows = symbols).
 struct GemvEpi {
-  int mode;                 // 0 / 1 as above
+  int mode;                 // 0 / 1 / 2 as above
   int taps;                 // EPI 1
   float* acc;               // EPI 1: [B][taps][E]
   const int* npos;          // EPI 1: position counter source: n = npos[row] - 1
@@ -119,42 +151,51 @@ struct GemvEpi {
 
 template <bool GELU>
 __device__ void gemv_phase(const float* Wslice /* rows o_lo.. of W, shared or global */, const float* __restrict__ bias,
-                           int o_lo, int o_hi, int K, int w_ld, const float* src, long long src_stride,
-                           const int* src_index /* optional: source row = src_index[row] */, const int* rows, int nrows,
+                           int o_lo, int o_hi, int K, int w_ld, const float* src, int src_stride,
+                           const int* rows /* optional: list of row ids; none = rows 0 .. nrows-1 */, int nrows,
                            float* __restrict__ out, long long out_stride, GemvEpi epi, float* xstage) {
   if (o_lo >= o_hi) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kBuf = kRG * 32 * kJ;       // float4 per staging buffer
   const int K4 = K >> 2;
   const int nchunks = (K4 + 32 * kJ - 1) / (32 * kJ);
-  // this warp's private staging buffer: kRG rows x (32 kJ) float4.  The group's activations travel L2 -> shared memory
-  // with cp.async (no registers held while in flight) once per row group when one chunk covers K, and every output
-  // block then reads them from shared memory instead of paying another exposed L2 round trip.
-  float4* xs = reinterpret_cast<float4*>(xstage) + warp * (kRG * 32 * kJ);
-  const int taps = epi.mode == 1 ? epi.taps : 1;
+  // This warp's two private staging buffers of kRG rows x (32 kJ) float4.  A chunk of a row group's activations travels
+  // L2 -> shared memory with cp.async (no registers held while in flight); every lane copies exactly the elements it
+  // reads back itself, so the buffers need no intra-warp synchronisation.  The NEXT chunk / row group is requested
+  // before the current one is consumed: one exposed L2 round trip per phase instead of one per chunk.
+  float4* xs = reinterpret_cast<float4*>(xstage) + warp * (2 * kBuf);
+  const int taps = epi.mode != 0 ? epi.taps : 1;
   const int nvirt = (o_hi - o_lo) * taps;
-  for (int g = warp; g * kRG < nrows; g += kThreads / 32) {
-    int rid[kRG];
-    long long soff[kRG];
+  int g = warp;
+  if (g * kRG >= nrows) return;
+  auto load_rows = [&](int gg, int (&rid)[kRG]) {
 #pragma unroll
     for (int r = 0; r < kRG; ++r) {
-      rid[r] = __ldcg(rows + min(g * kRG + r, nrows - 1));        // tail rows repeat the last one
-      soff[r] = static_cast<long long>(src_index ? __ldcg(src_index + rid[r]) : rid[r]) * src_stride;
+      const int ri = min(gg * kRG + r, nrows - 1);                // tail rows repeat the last one
+      rid[r] = rows ? __ldcg(rows + ri) : ri;
     }
-    // activations are produced by other CTAs during this kernel: read them through L2 (ld.global.cg), never L1
-    // activations are produced by other CTAs during this kernel: they are read through L2 (cp.async.cg), never L1
-    auto stage_x = [&](int c) {
-      __syncwarp();                                   // everybody is done reading the previous contents
+  };
+  // activations are produced by other CTAs during this kernel: they are read through L2 (cp.async.cg), never L1
+  auto issue = [&](const int (&rid)[kRG], int c, int buf) {
 #pragma unroll
-      for (int r = 0; r < kRG; ++r)
+    for (int r = 0; r < kRG; ++r)
 #pragma unroll
-        for (int j = 0; j < kJ; ++j) {
-          const int f = (c * kJ + j) * 32 + lane;
-          if (f < K4) cp_async16(xs + (r * kJ + j) * 32 + lane, reinterpret_cast<const float4*>(src + soff[r]) + f);
-        }
-      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-    };
-    if (nchunks == 1) stage_x(0);
+      for (int j = 0; j < kJ; ++j) {
+        const int f = (c * kJ + j) * 32 + lane;
+        if (f < K4)
+          cp_async16(xs + buf * kBuf + (r * kJ + j) * 32 + lane,
+                     reinterpret_cast<const float4*>(src + static_cast<long long>(rid[r]) * src_stride) + f);
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int rid[kRG], rid_next[kRG];
+  load_rows(g, rid);
+  issue(rid, 0, 0);
+  int buf = 0;
+  for (; g * kRG < nrows; g += kWarps) {
+    const bool has_next = (g + kWarps) * kRG < nrows;
+    if (has_next) load_rows(g + kWarps, rid_next);
     for (int vb = 0; vb < nvirt; vb += kOB) {
       float acc[kRG * kOB];
 #pragma unroll
@@ -162,25 +203,36 @@ __device__ void gemv_phase(const float* Wslice /* rows o_lo.. of W, shared or gl
       // epilogue operand of this lane's (row, output): requested now, its L2 round trip hides under the FMAs
       const int er = lane / kOB, evo = vb + lane % kOB;
       const bool e_ok = g * kRG + er < nrows && evo < nvirt;
+      int erow = rid[0];
+#pragma unroll
+      for (int r = 1; r < kRG; ++r) erow = (er == r) ? rid[r] : erow;
       float* slot = nullptr;
       float prev = 0.f;
       if (epi.mode == 1 && e_ok) {
-        int erow = rid[0];
-#pragma unroll
-        for (int r = 1; r < kRG; ++r) erow = (er == r) ? rid[r] : erow;
         const int n = __ldcg(epi.npos + erow) - 1;               // position of the new input vector
         slot = epi.acc + (static_cast<long long>(erow) * taps + (n + taps - 1 - evo % taps) % taps) * epi.E + o_lo + evo / taps;
         prev = __ldcg(slot);                                     // only this CTA ever touches (row, *, o)
       }
-      for (int f0 = 0; f0 < K4; f0 += 32 * kJ) {
-        if (nchunks > 1) stage_x(f0 / (32 * kJ));
+      for (int c = 0; c < nchunks; ++c) {
+        // a new staging buffer becomes current: per chunk when a row spans several chunks (then every output block
+        // re-stages), else once per row group; request its successor first, then wait for the current one only
+        if (nchunks > 1 || vb == 0) {
+          bool pf = true;
+          if (nchunks > 1 && c + 1 < nchunks) issue(rid, c + 1, buf ^ 1);
+          else if (nchunks > 1 && vb + kOB < nvirt) issue(rid, 0, buf ^ 1);
+          else if (has_next) issue(rid_next, 0, buf ^ 1);
+          else pf = false;
+          if (pf) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const int f0 = c * 32 * kJ;
         float4 x[kRG][kJ];        // (live inside one output block only: kept across blocks, ptxas spills 4 KB)
 #pragma unroll
         for (int r = 0; r < kRG; ++r)
 #pragma unroll
           for (int j = 0; j < kJ; ++j) {
             const int f = f0 + j * 32 + lane;
-            x[r][j] = f < K4 ? xs[(r * kJ + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[r][j] = f < K4 ? xs[buf * kBuf + (r * kJ + j) * 32 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
         for (int o = 0; o < kOB; ++o) {
@@ -205,27 +257,30 @@ __device__ void gemv_phase(const float* Wslice /* rows o_lo.. of W, shared or gl
             }
           }
         }
+        if (nchunks > 1) buf ^= 1;
       }
       const float tot = warp_transpose_reduce(acc);     // lane l: total of partial l = (row l / kOB, output l % kOB)
       if (e_ok) {
         const int o = o_lo + evo / taps;
-        int row = rid[0];
-#pragma unroll
-        for (int r = 1; r < kRG; ++r) row = (er == r) ? rid[r] : row;
         if (epi.mode == 0) {
           float v = tot + (bias ? __ldg(bias + o) : 0.f);
           if (GELU) v = gelu_erf(v);
-          out[row * out_stride + o] = v;
+          out[erow * out_stride + o] = v;
+        } else if (epi.mode == 2) {
+          out[erow * out_stride + static_cast<long long>(evo % taps) * epi.E + o] = tot;
         } else if (evo % taps == taps - 1) {                     // newest tap: position n is complete
           float v = prev + tot + __ldg(bias + o);
           if (GELU) v = gelu_erf(v);
-          out[row * out_stride + o] = v;
+          out[erow * out_stride + o] = v;
           *slot = 0.f;                                           // the slot next collects position n + taps
         } else {
           *slot = prev + tot;
         }
       }
     }
+    if (nchunks == 1) buf ^= 1;
+#pragma unroll
+    for (int r = 0; r < kRG; ++r) rid[r] = rid_next[r];
   }
 }
 
@@ -262,6 +317,40 @@ __device__ __forceinline__ void block_argmax(float best, float second, int idx, 
     if (lane == 0) { s_best[0] = best; s_second[0] = second; s_idx[0] = idx; }
   }
   __syncthreads();
+}
+
+// conv1 (kernel size 3) for ONE utterance whose newest symbol `tok` sits at position n, by the whole CTA: tap j of the
+// symbol's table row lands in the accumulator of position n + 2 - j; the newest tap completes position n (bias + GELU ->
+// ynew) and clears its slot for position n + 3.  Same arithmetic, in the same order, as the tap-accumulating GEMV
+// epilogue (EPI 1) that conv2 uses.  acc1 / t1 are written by other CTAs in other steps: L2 loads only.
+__device__ __forceinline__ void conv1_update(const DecodeArgs& p, int b, int tok, int n) {
+  const int E = p.E;
+  const float* trow = p.t1 + static_cast<long long>(tok) * 3 * E;
+  float* acc = p.acc1 + static_cast<long long>(b) * 3 * E;
+  float* slot[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) slot[j] = acc + ((n + 2 - j) % 3) * E;
+  for (int o0 = threadIdx.x; o0 < E; o0 += 2 * kThreads) {
+    // all twelve L2 loads of this thread's two channels are in flight before the first store
+    float a[2][3], t[2][3], bb[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int o = min(o0 + q * kThreads, E - 1);
+      bb[q] = __ldg(p.b1 + o);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { a[q][j] = __ldcg(slot[j] + o); t[q][j] = __ldcg(trow + j * E + o); }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int o = o0 + q * kThreads;
+      if (o < E) {
+        slot[0][o] = a[q][0] + t[q][0];
+        slot[1][o] = a[q][1] + t[q][1];
+        p.ynew[static_cast<long long>(b) * E + o] = gelu_erf(a[q][2] + t[q][2] + bb[q]);
+        slot[2][o] = 0.f;
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p) {
@@ -326,22 +415,25 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
   for (int v = cta; v < p.NS; v += G)
     block_layer_norm(p.emb + static_cast<long long>(v) * E, p.ln1_w, p.ln1_b, p.emb_ln + static_cast<long long>(v) * E, E, red);
   grid_barrier(bar_counter, bar_target);
+  // ---- conv1 tap table: t1[v][j][o] = W1_j[o, :] . LN(emb[v]) for every symbol v (this CTA's output channels)
+  {
+    GemvEpi epi{2, 3, nullptr, nullptr, E};
+    gemv_phase<false>(w1_s, nullptr, e_lo, e_hi, E, 3 * E, p.emb_ln, E, nullptr, p.NS, p.t1, 3 * E, epi, xstage);
+  }
+  lap(3);
+  grid_barrier(bar_counter, bar_target);
+  // ---- the seed blank at position 0 of every utterance
+  for (int b = cta; b < B; b += G) conv1_update(p, b, p.blank, 0);
+  grid_barrier(bar_counter, bar_target);
+  lap(7);
 
   for (int step = 0;; ++step) {
     const int n_emit = __ldcg(counts + 1);
     if (n_emit > 0) {
-      // ---- P4: conv1, tap products of the new symbol's layer-normed embedding (row last_tok[b] of the table)
-      {
-        GemvEpi epi{1, 3, p.acc1, p.ntok, E};
-        gemv_phase<true>(w1_s, p.b1, e_lo, e_hi, E, 3 * E, p.emb_ln, E, p.last_tok, rows_emit, n_emit, p.ynew, E, epi, xstage);
-      }
-      lap(3);
-      grid_barrier(bar_counter, bar_target);
-      lap(7);
       // ---- P5: conv2, tap products of the new conv1 output
       {
         GemvEpi epi{1, 5, p.acc2, p.ntok, E};
-        gemv_phase<true>(w2_s, p.b2, e_lo, e_hi, E, 5 * E, p.ynew, E, nullptr, rows_emit, n_emit, p.z, E, epi, xstage);
+        gemv_phase<true>(w2_s, p.b2, e_lo, e_hi, E, 5 * E, p.ynew, E, rows_emit, n_emit, p.z, E, epi, xstage);
       }
       lap(4);
       grid_barrier(bar_counter, bar_target);
@@ -349,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
       // ---- P6: linear
       {
         GemvEpi epi{0, 1, nullptr, nullptr, E};
-        gemv_phase<false>(wl_s, p.bl, l_lo, l_hi, E, E, p.z, E, nullptr, rows_emit, n_emit, p.lin, H, epi, xstage);
+        gemv_phase<false>(wl_s, p.bl, l_lo, l_hi, E, E, p.z, E, rows_emit, n_emit, p.lin, H, epi, xstage);
       }
       lap(5);
       grid_barrier(bar_counter, bar_target);
@@ -392,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
     // ---- P2: joint logits for the active rows
     {
       GemvEpi epi{0, 1, nullptr, nullptr, E};
-      gemv_phase<false>(Wj_s, p.bj, j_lo, j_hi, H, H, p.hbuf, H, nullptr, rows_act, n_act, p.logits, V, epi, xstage);
+      gemv_phase<false>(Wj_s, p.bj, j_lo, j_hi, H, H, p.hbuf, H, rows_act, n_act, p.logits, V, epi, xstage);
     }
     lap(1);
     grid_barrier(bar_counter, bar_target);
@@ -413,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
       // torch.argmax always returns an in-range index; a row without any finite maximum (all NaN / -inf) maps to 0
       const int tok = static_cast<unsigned>(s_idx[0]) < static_cast<unsigned>(V) ? s_idx[0] : 0;
       const bool advance = (tok == p.blank) || (__ldcg(p.per + b) >= p.max_per_frame);
+      const int nt_old = __ldcg(p.ntok + b);        // every thread reads it before thread 0 bumps it
       __syncthreads();
       if (tid == 0) {
         if (p.margins) p.margins[static_cast<long long>(step) * B + b] = s_best[0] - s_second[0];
@@ -425,6 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) greedy_decode_kernel(DecodeArgs p
           rows_emit[atomicAdd(&counts[1], 1)] = b;
         }
       }
+      if (!advance) conv1_update(p, b, tok, nt_old);   // the new symbol's position in the predictor's input = old ntok
       __syncthreads();
     }
     // (a finished utterance may keep emit = 1; P1 then recomputes the same feats from an unchanged lin -- harmless)
@@ -447,7 +541,8 @@ constexpr size_t kBarBytes = 128;      // reserved (a counter line for a hand-ro
 size_t greedy_decode_scratch_bytes(int B, int H, int V, int E) {
   const size_t b = static_cast<size_t>(B);
   const size_t floats = 3 * pad4(b * H) /*feats, hbuf, lin*/ + pad4(b * V) /*logits*/ + pad4(b * 3 * E) + pad4(b * 5 * E) +
-                        2 * pad4(b * E) /*ynew, z*/ + pad4(static_cast<size_t>(V) * E) /*LayerNorm(embedding) table*/;
+                        2 * pad4(b * E) /*ynew, z*/ + pad4(static_cast<size_t>(V) * E) /*LayerNorm(embedding) table*/ +
+                        pad4(static_cast<size_t>(V) * 3 * E) /*conv1 tap table*/;
   const size_t ints = b * 6 + 16;
   return kTimerBytes + kBarBytes + floats * 4 + ints * 4 + 256;
 }
@@ -459,14 +554,16 @@ int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream) {
   const int grid = device_sm_count();
   // Weight residency: each CTA keeps its output slice of a matrix in shared memory if it fits the budget, in the order
   // joint (read every step), conv2, conv1, linear; whatever does not fit is streamed from L2 every step instead.
-  const size_t xstage_bytes = static_cast<size_t>(kThreads / 32) * kRG * 32 * kJ * sizeof(float4);   // 64 KB
+  const size_t xstage_bytes = 2 * static_cast<size_t>(kThreads / 32) * kRG * 32 * kJ * sizeof(float4);   // 2 x 64 KB
   const size_t budget = 220 * 1024 - xstage_bytes;
   auto per = [&](int n) { return static_cast<size_t>((n + grid - 1) / grid); };
   const size_t need[4] = {per(a.V) * a.H * 4, per(a.E) * 5 * a.E * 4, per(a.E) * 3 * a.E * 4, per(a.H) * a.E * 4};
   size_t smem = 0;
   a.resident = 0;
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {
+    if (i == 2) continue;    // conv1's weights are only read once, for the tap table at kernel start
     if (smem + need[i] <= budget) { smem += need[i]; a.resident |= 1 << i; }
+  }
   a.weight_floats = static_cast<int>(smem / sizeof(float));
   smem += xstage_bytes;
   // carve the scratch
@@ -487,6 +584,7 @@ int launch_greedy_decode(DecodeArgs a, float* scratch, cudaStream_t stream) {
   a.z = f; f += pad4(b * E);
   a.lin = f; f += pad4(b * H);
   a.emb_ln = f; f += pad4(static_cast<size_t>(a.NS) * E);
+  a.t1 = f; f += pad4(static_cast<size_t>(a.NS) * 3 * E);
   int* ip = reinterpret_cast<int*>(f);
   a.t_idx = ip; ip += B;
   a.per = ip; ip += B;

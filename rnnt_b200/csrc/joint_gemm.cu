@@ -45,7 +45,7 @@ constexpr int kNumProdWarps = 8;
 constexpr int kThreadsNoProd = 32 * kFirstProdWarp;                     // 320
 constexpr int kThreadsProd = 32 * (kFirstProdWarp + kNumProdWarps);     // 576
 constexpr int kTmemCols = 512;
-constexpr int kScratchSlots = 4;   // per-CTA activation scratch (h_map 2): tiles in flight <= 3
+constexpr int kScratchSlots = 2;   // per-CTA activation scratch (h_map 2): unit n is stored only after unit n-2 is consumed
 
 struct SmemLayout {
   static constexpr int ring = 0;

@@ -93,11 +93,11 @@ struct DecodeArgs {
   int* tokens;             // (B, max_len) emitted tokens (seed blank excluded)
   int* ntok;               // (B) 1 + number of emitted tokens
   // scratch (carved by the launcher)
-  float *feats, *hbuf, *logits, *acc1, *acc2, *ynew, *z, *lin, *emb_ln, *margins;
+  float *feats, *hbuf, *logits, *acc1, *acc2, *ynew, *z, *lin, *emb_ln, *t1 /* conv1 tap table (NS, 3E) */, *margins;
   int *t_idx, *per, *emit, *rows, *last_tok, *flags;
   unsigned* bar;           // grid-barrier counters (one per 128-byte line)
   int NS;                  // number of symbols = rows of the embedding table
-  long long* prof;         // 8 cycle counters (block 0): P1, P2, P3, P4, P5, P6, -, grid barriers
+  long long* prof;         // 8 cycle counters (block 0): P1, P2, P3, conv1 table build (once), P5, P6, -, grid barriers
 };
 
 size_t greedy_decode_scratch_bytes(int B, int H, int V, int E);
