@@ -208,6 +208,8 @@ __device__ void gemv_phase(const float* Wslice /* rows o_lo.. of W, shared or gl
       for (int r = 1; r < kRG; ++r) erow = (er == r) ? rid[r] : erow;
       float* slot = nullptr;
       float prev = 0.f;
+      // (the grid barrier's fences drop the L1 lines, so even the bias is an L2 access once per phase and block)
+      const float bias_v = (e_ok && bias) ? __ldg(bias + o_lo + evo / taps) : 0.f;
       if (epi.mode == 1 && e_ok) {
         const int n = __ldcg(epi.npos + erow) - 1;               // position of the new input vector
         slot = epi.acc + (static_cast<long long>(erow) * taps + (n + taps - 1 - evo % taps) % taps) * epi.E + o_lo + evo / taps;
@@ -263,13 +265,13 @@ __device__ void gemv_phase(const float* Wslice /* rows o_lo.. of W, shared or gl
       if (e_ok) {
         const int o = o_lo + evo / taps;
         if (epi.mode == 0) {
-          float v = tot + (bias ? __ldg(bias + o) : 0.f);
+          float v = tot + bias_v;
           if (GELU) v = gelu_erf(v);
           out[erow * out_stride + o] = v;
         } else if (epi.mode == 2) {
           out[erow * out_stride + static_cast<long long>(evo % taps) * epi.E + o] = tot;
         } else if (evo % taps == taps - 1) {                     // newest tap: position n is complete
-          float v = prev + tot + __ldg(bias + o);
+          float v = prev + tot + bias_v;
           if (GELU) v = gelu_erf(v);
           out[erow * out_stride + o] = v;
           *slot = 0.f;                                           // the slot next collects position n + taps
