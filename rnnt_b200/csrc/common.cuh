@@ -248,6 +248,34 @@ __device__ __forceinline__ float lg2_approx(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (FFMA2 / FADD2 on sm_100: one issue slot for two lanes of work) and the 3-input max (FMNMX3).  The
+// operands are adjacent registers of the tcgen05.ld result, so the b64 moves cost nothing.
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a, float b0, float b1) {   // x = x * a + b
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %2};\n\tmov.b64 rc, {%3, %4};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(a), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& x0, float& x1, float b0, float b1) {            // x = x + b
+  asm("{.reg .b64 ra, rc, rd;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rc, {%2, %3};\n\t"
+      "add.rn.f32x2 rd, ra, rc;\n\tmov.b64 {%0, %1}, rd;}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& x0, float& x1, float a) {                        // x = x * a
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %2};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "+f"(x0), "+f"(x1)
+      : "f"(a));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -52,7 +52,9 @@ struct SmemLayout {
   static constexpr int xchg = ring + kStages * kStageBytes;   // F: set-1 -> set-0 softmax partials (2 x 128 x 16 B)
   static constexpr int bars = xchg + 2 * kTileM * 16;
   // producers, T-contiguous encoder layout: per half-tile a double-buffered 16(t) x 64(k) fp32 transposing stage
-  static constexpr int enc_stage = bars + 256;
+  // epilogue: bias * log2e of the pass a set is draining, double-buffered per set (2 sets x 2 x 256 floats)
+  static constexpr int bias_stage = bars + 256;
+  static constexpr int enc_stage = bias_stage + 2 * 2 * kBN * 4;
   static constexpr int total_noprod = enc_stage;
   static constexpr int total = enc_stage + 2 * 2 * kTileT * kBK * 4;
 };
@@ -269,6 +271,16 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 
       for (int pass = 0; pass < npass; ++pass, ++pc) {
         if (static_cast<int>(pc & 1) != eset) continue;
+        // this pass's 256 bias values -> shared memory (requested before the wait for the accumulator; the L1 is a few
+        // KB next to 220 KB of shared memory and the producers stream through it, so per-chunk __ldg's of the bias were
+        // L2 round trips on the drain's critical path).  Buffer (pc >> 1) & 1 of this set: the set's barrier of pass
+        // j orders every warp's reads of pass j-1 before any write of pass j+1.
+        float* bias_s = reinterpret_cast<float*>(smem_gen + SL::bias_stage) + (eset * 2 + ((pc >> 1) & 1)) * kBN;
+        {
+          const int i2 = (lane_grp * 32 + lane) * 2;
+          *reinterpret_cast<float2*>(bias_s + i2) = __ldg(reinterpret_cast<const float2*>(p.bias2 + pass * kBN + i2));
+        }
+        named_bar_sync(1 + eset, 128);
         mbar_wait(tmem_full + 8 * eset, (pc >> 1) & 1);
         tc_fence_after();
         const int nchunk = ((p.dbg & 1) || !mine) ? 0 : (kBN / 32);
@@ -277,31 +289,41 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           float v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + eset * kBN + c32 * 32, v);
           tmem_ld_wait();
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias2 + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c32 * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 bb = __ldg(b4 + q);
-            v[4 * q + 0] = fmaf(v[4 * q + 0], kLog2e, bb.x);
-            v[4 * q + 1] = fmaf(v[4 * q + 1], kLog2e, bb.y);
-            v[4 * q + 2] = fmaf(v[4 * q + 2], kLog2e, bb.z);
-            v[4 * q + 3] = fmaf(v[4 * q + 3], kLog2e, bb.w);
+            const float4 bb = b4[q];
+            fma2(v[4 * q + 0], v[4 * q + 1], kLog2e, bb.x, bb.y);
+            fma2(v[4 * q + 2], v[4 * q + 3], kLog2e, bb.z, bb.w);
           }
           if (MODE == 0) {
-            float cmax = v[0];
+            // online softmax over the chunk: 16 three-input maxima, then (v - m) / sum as packed pairs
+            float cmax = max3(v[0], v[1], v[2]);
 #pragma unroll
-            for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
-            const float m_new = fmaxf(m, cmax);
-            float acc = 0.f;
+            for (int j = 3; j < 31; j += 2) cmax = max3(cmax, v[j], v[j + 1]);
+            const float m_new = fmaxf(m, fmaxf(cmax, v[31]));
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc += ex2_approx(v[j] - m_new);
+            for (int j = 0; j < 32; j += 2) {
+              float e0 = v[j], e1 = v[j + 1];
+              add2(e0, e1, -m_new, -m_new);
+              add2(s0, s1, ex2_approx(e0), ex2_approx(e1));
+            }
+            const float acc = s0 + s1;
             ssum = ssum * ex2_approx(m - m_new) + acc;
             m = m_new;
             // label / blank logits: only the one chunk that holds the column pays for the selection
             if (static_cast<unsigned>(tgt - col0) < 32u) x_tgt = pick32(v, tgt - col0);
             if (static_cast<unsigned>(p.blank - col0) < 32u) x_blank = pick32(v, p.blank - col0);
           } else {
+            // softmax * gamma = 2^(x - lse) * gamma, as packed pairs around the two MUFU operations
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ex2_approx(v[j] - lse2) * gam;
+            for (int j = 0; j < 32; j += 2) {
+              add2(v[j], v[j + 1], -lse2, -lse2);
+              v[j] = ex2_approx(v[j]);
+              v[j + 1] = ex2_approx(v[j + 1]);
+              mul2(v[j], v[j + 1], gam);
+            }
             if (p.clamp > 0.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -cbound), cbound);
