@@ -303,12 +303,13 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// tile -> utterance lookup: largest b with tile_off[b] <= tile (tile_off has B+1 entries)
-__device__ __forceinline__ int find_utt(const int* __restrict__ tile_off, int B, int tile) {
+// tile -> utterance lookup: largest b with tile_off[b] <= tile (tile_off has B+1 entries).  Plain loads: the table
+// may be the kernel's shared-memory copy (stage_len_tables) or the global one.
+__device__ __forceinline__ int find_utt(const int* tile_off, int B, int tile) {
   int lo = 0, hi = B;  // invariant: tile_off[lo] <= tile < tile_off[hi]
   while (hi - lo > 1) {
     int mid = (lo + hi) >> 1;
-    if (__ldg(tile_off + mid) <= tile) lo = mid; else hi = mid;
+    if (tile_off[mid] <= tile) lo = mid; else hi = mid;
   }
   return lo;
 }
@@ -317,19 +318,41 @@ struct TileCoord {
   int b, t0, u0, Tb, Ub;
 };
 // half-tile id -> utterance, first frame t0, first label position u0, and the utterance's lengths
-__device__ __forceinline__ TileCoord decode_half(const int* __restrict__ tile_off, const int* __restrict__ T_len,
-                                                 const int* __restrict__ U_len, int B, int T, int U1, int half_id) {
+__device__ __forceinline__ TileCoord decode_half(const int* tile_off, const int* T_len, const int* U_len, int B, int T,
+                                                 int U1, int half_id) {
   TileCoord c;
   c.b = find_utt(tile_off, B, half_id);
   // same clamp as tile_table_kernel / lattice_kernel / coef_kernel: an out-of-range length (reported through the status
   // word, which poisons the costs with NaN) must not desynchronise the tile enumeration or index past `targets`
-  c.Tb = max(1, min(__ldg(T_len + c.b), T));
-  c.Ub = max(0, min(__ldg(U_len + c.b), U1 - 1));
+  c.Tb = max(1, min(T_len[c.b], T));
+  c.Ub = max(0, min(U_len[c.b], U1 - 1));
   const int nu = (c.Ub + 1 + kHalfU - 1) / kHalfU;
-  const int local = half_id - __ldg(tile_off + c.b);
+  const int local = half_id - tile_off[c.b];
   c.t0 = (local / nu) * kTileT;
   c.u0 = (local % nu) * kHalfU;
   return c;
+}
+
+// The three per-utterance tables every tile decode walks (binary search over tile_off, then the lengths), copied to
+// shared memory once per CTA: the GEMM kernels leave the L1 a few KB next to > 200 KB of shared memory, so each step of
+// that dependent chain was an L2 round trip in front of an accumulator drain.  Falls back to the global tables for
+// B > kLenTabMaxB.  The caller synchronises the CTA before the first use.
+constexpr int kLenTabMaxB = 340;
+constexpr int kLenTabBytes = (3 * kLenTabMaxB + 1) * 4 + 12;       // 4096
+struct LenTables {
+  const int* tile_off;
+  const int* T_len;
+  const int* U_len;
+};
+__device__ __forceinline__ LenTables stage_len_tables(int* tab, const int* tile_off, const int* T_len, const int* U_len,
+                                                      int B) {
+  if (B > kLenTabMaxB) return LenTables{tile_off, T_len, U_len};
+  for (int i = threadIdx.x; i <= B; i += blockDim.x) tab[i] = __ldg(tile_off + i);
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    tab[B + 1 + i] = __ldg(T_len + i);
+    tab[2 * B + 1 + i] = __ldg(U_len + i);
+  }
+  return LenTables{tab, tab + B + 1, tab + 2 * B + 1};
 }
 
 }  // namespace rb

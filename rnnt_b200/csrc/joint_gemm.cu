@@ -54,7 +54,8 @@ struct SmemLayout {
   // producers, T-contiguous encoder layout: per half-tile a double-buffered 16(t) x 64(k) fp32 transposing stage
   // epilogue: bias * log2e of the pass a set is draining, double-buffered per set (2 sets x 2 x 256 floats)
   static constexpr int bias_stage = bars + 256;
-  static constexpr int enc_stage = bias_stage + 2 * 2 * kBN * 4;
+  static constexpr int len_tab = bias_stage + 2 * 2 * kBN * 4;   // tile_off / T_len / U_len copies (stage_len_tables)
+  static constexpr int enc_stage = len_tab + kLenTabBytes;
   static constexpr int total_noprod = enc_stage;
   static constexpr int total = enc_stage + 2 * 2 * kTileT * kBK * 4;
 };
@@ -144,6 +145,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
     tmem_relinquish_pair();
   }
+  const LenTables lt = stage_len_tables(reinterpret_cast<int*>(smem_gen + SL::len_tab), p.tile_off, p.T_len, p.U_len, p.B);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();      // barrier inits and TMEM allocation of both CTAs are visible before any remote arrive
@@ -241,7 +243,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       const int q = base_ + rank;
       const bool mine = q < nunits;
       const int hid = half_id(q, sub);
-      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, p.T, p.U1, max(hid, 0));
+      const TileCoord tc = decode_half(lt.tile_off, lt.T_len, lt.U_len, p.B, p.T, p.U1, max(hid, 0));
       const int t = tc.t0 + ti, u = tc.u0 + ui;
       const bool valid = hid >= 0 && (t < tc.Tb) && (u <= tc.Ub);
       const long long cell = (static_cast<long long>(tc.b) * p.T + min(t, p.T - 1)) * p.U1 + min(u, p.U1 - 1);
@@ -397,7 +399,7 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (lane == 0) mbar_arrive(h_ready + 8 * (cnt & 1));
         continue;
       }
-      const TileCoord tc = decode_half(p.tile_off, p.T_len, p.U_len, p.B, p.T, p.U1, hid);
+      const TileCoord tc = decode_half(lt.tile_off, lt.T_len, lt.U_len, p.B, p.T, p.U1, hid);
       const int row0 = h_row0(q, sub, hid, cnt);
       const float* e_ptr[2];
       const float* p_ptr[2];
