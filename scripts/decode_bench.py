@@ -29,4 +29,4 @@ for bias, lo in ((1.0, 200), (1.8, 300)):
     ref = model.greedy_decode_features(feats, lens, max_length=200, engine="graph")
     print(f"bias {bias}: {best*1e3:.2f} ms, ~{steps} steps, {best*1e6/steps:.1f} us/step, tokens {sum(len(x) for x in toks)}, "
           f"graph-engine identical: {ref == toks}")
-    print("   phase cycles P1..P6,-,barriers:", cyc, " sum us @1.9GHz:", sum(cyc) / 1.9e3)
+    print("   phase cycles P1,P2,P3,conv1-table(once),P5,P6,steps,barriers:", cyc, " sum us @1.9GHz:", sum(cyc) / 1.9e3)
