@@ -298,10 +298,9 @@ def other_configs(torch, dev):
     out["greedy_decode_B64_T400"] = dict(
         ms_total=best * 1e3, frames=frames, frames_per_s=frames / best, tokens=ntok, steps=steps,
         us_per_step=best * 1e6 / steps, weight_bytes_per_step=w_bytes, l2_gbs=w_bytes * steps / best / 1e9,
-        bound="latency / shared-memory bandwidth: one cooperative kernel, 5 grid barriers per emitting step (1.2 us each + "
-              "load imbalance); the fp32 weights (11.5 MB: joint, conv2, linear) are resident in shared memory (82 KB "
-              "per SM), conv1 is a per-symbol table built at kernel start, a step only moves activations through L2; "
-              "the GEMV phases are bound by the shared-memory reads of the weight slices (48 LDS.128 per 512 FFMA), so "
+        bound="latency: one cooperative kernel, 5 grid barriers per emitting step (1.2 us each + waiting for the slowest "
+              "CTA of the phase); the fp32 weights (11.5 MB: joint, conv2, linear) are resident in shared memory (82 KB "
+              "per SM), conv1 is a per-symbol table built at kernel start, a step only moves activations through L2, so "
               "neither HBM nor the tensor pipe is the limit",
         phase_cycles=dict(zip(["P1", "P2", "P3", "conv1_table_build", "P5", "P6", "steps", "grid_barriers"], cyc)),
         tokens_match_cpu_reference=[toks[i] == ref_toks[i] for i in range(n_ref)],
