@@ -737,6 +737,24 @@ def test_decode_single_utterance_odd_vocab():
     assert rnnt_b200.functional._last_decode_phase_cycles is not None
 
 
+def test_decode_wide_batch_odd_sizes():
+    """More utterances than one pass of row groups (several prefetched groups per warp), an embedding width that does
+    not fill a staging chunk, more symbols than CTAs (tail groups in the conv1 table build), ragged lengths."""
+    import rnnt_b200
+    torch.manual_seed(11)
+    B, T, H, V, E = 150, 24, 96, 301, 72
+    joint = rnnt_b200.JointNetwork(-1, -1, H, V)
+    with torch.no_grad():
+        joint.joint_ln.weight.mul_(3.0)
+        joint.joint_ln.bias[V - 1] += 1.2
+    model = rnnt_b200.RNNTModel(rnnt_b200.ConvPredictor(V, H, E, 0.3), torch.nn.Identity(), joint).cuda().eval()
+    feats = torch.randn(B, T, H, device="cuda")
+    lens = torch.randint(1, T + 1, (B,)); lens[0] = T
+    got = model.greedy_decode_features(feats, lens, max_length=30)
+    assert got == model.greedy_decode_features(feats, lens, max_length=30, engine="graph")
+    assert sum(len(x) for x in got) > B          # the workload does emit
+
+
 def test_greedy_decode_dispatches_on_predictor_shape():
     """RNNTModel.greedy_decode (rnnt/model.py:130-139) accepts any ConvPredictor-SHAPED module (e.g. the reference's own
     class when only joint._target_ is swapped), runs LSTMPredictor-shaped ones through the stateful loop
