@@ -80,6 +80,19 @@ def test_fuzz_small_ragged_shapes_vs_cpu_reference():
             assert r <= GRAD_TOL_FP32 or a < 1e-5, ((B, T, U, H, V), k, r, a)
 
 
+def test_many_utterances_fall_back_to_global_tile_tables():
+    """B above the shared-memory tile-table capacity (340 utterances): the kernels walk the global tables instead."""
+    inp = make_inputs(400, 6, 3, 64, 40, ragged=True, seed=77)
+    ref = torch_reference(inp, device="cpu")
+    out = fused_raw(inp)
+    assert out["status"] == 0
+    err = (out["costs"].cpu() - ref["costs"]).abs()
+    assert (err <= LOSS_RTOL * ref["costs"].abs() + 3e-4).all()
+    for k in ("d_enc", "d_pred", "dW", "db"):
+        r, a = rel_err(out[k].cpu(), ref[k])
+        assert r <= GRAD_TOL_FP32 or a < 1e-5, (k, r, a)
+
+
 def test_multi_chunk_backward_equals_single_chunk():
     inp = make_inputs(2, 40, 20, 256, 1024, ragged=True)
     one = fused_raw(inp)
