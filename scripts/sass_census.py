@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "rnnt_b200", "_C", "librnnt_b200.so")
 PATTERNS = ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UTCBAR",
             "SYNCS", "HMMA", "HGMMA", "LDGSTS", "MUFU.TANH", "MUFU.EX2", "MUFU.LG2", "RED.E", "REDG", "ATOMG", "ATOM",
-            "FFMA", "BAR.SYNC", "UCGABAR"]
+            "FFMA2", "FADD2", "FMUL2", "FMNMX3", "FFMA", "BAR.SYNC", "UCGABAR"]
 
 
 def main():
