@@ -56,7 +56,10 @@ struct SmemLayout {
   static constexpr int bias_stage = bars + 256;
   static constexpr int len_tab = bias_stage + 2 * 2 * kBN * 4;   // tile_off / T_len / U_len copies (stage_len_tables)
   static constexpr int enc_stage = len_tab + kLenTabBytes;
-  static constexpr int total_noprod = enc_stage;
+  // G without producers: per epilogue warp a 32-row x 64-byte transposing stage for the gradient stores (same offset as
+  // the producers' stage, which that kernel does not have)
+  static constexpr int g_stage = enc_stage;
+  static constexpr int total_noprod = g_stage + kNumEpiWarps * 32 * 64;
   static constexpr int total = enc_stage + 2 * 2 * kTileT * kBK * 4;
 };
 
@@ -330,21 +333,50 @@ joint_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -cbound), cbound);
             }
-            // fp16 (scaled by S through the coefficients) straight to the gradient ring: 64 contiguous bytes per row
-            uint4* dst = reinterpret_cast<uint4*>(g_row + col0);
+            uint4 w4[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 w;
-              w.x = pack_f16x2(v[8 * q + 0], v[8 * q + 1]);
-              w.y = pack_f16x2(v[8 * q + 2], v[8 * q + 3]);
-              w.z = pack_f16x2(v[8 * q + 4], v[8 * q + 5]);
-              w.w = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
-              dst[q] = w;
+              w4[q].x = pack_f16x2(v[8 * q + 0], v[8 * q + 1]);
+              w4[q].y = pack_f16x2(v[8 * q + 2], v[8 * q + 3]);
+              w4[q].z = pack_f16x2(v[8 * q + 4], v[8 * q + 5]);
+              w4[q].w = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
             }
-            // the two columns with one-hot terms are patched afterwards (same thread, program order): their softmax
-            // probabilities are exp(lp) from the forward, so no per-element comparison is needed in the loop above
-            if (static_cast<unsigned>(p.blank - col0) < 32u) g_row[p.blank] = __float2half_rn(g_blank);
-            if (static_cast<unsigned>(tgt - col0) < 32u) g_row[tgt] = __float2half_rn(g_tgt);
+            if (!PRODUCE) {
+              // fp16 (scaled by S through the coefficients) to the gradient ring through a per-warp transposing stage:
+              // thread = row writes its 64 bytes (16-byte chunk c at c ^ (row >> 1), conflict-free), the one-hot columns
+              // are patched in place, then 4 lanes per row store 64 contiguous bytes -- 8 full-sector segments per
+              // instruction instead of 32 scattered 16-byte ones.
+              uint8_t* gs = smem_gen + SL::g_stage + (warp - kFirstEpiWarp) * (32 * 64);
+              __syncwarp();                                     // the previous chunk's read-back is complete
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(gs + lane * 64 + ((q ^ (lane >> 1)) & 3) * 16) = w4[q];
+              if (static_cast<unsigned>(p.blank - col0) < 32u) {
+                const int cc = p.blank - col0;
+                *reinterpret_cast<__half*>(gs + lane * 64 + (((cc >> 3) ^ (lane >> 1)) & 3) * 16 + (cc & 7) * 2) = __float2half_rn(g_blank);
+              }
+              if (static_cast<unsigned>(tgt - col0) < 32u) {
+                const int cc = tgt - col0;
+                *reinterpret_cast<__half*>(gs + lane * 64 + (((cc >> 3) ^ (lane >> 1)) & 3) * 16 + (cc & 7) * 2) = __float2half_rn(g_tgt);
+              }
+              __syncwarp();
+              __half* g_base = p.g_ring + (static_cast<long long>(q) * kTileM + lane_grp * 32) * p.Vp + col0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = 8 * i + (lane >> 2), c = lane & 3;
+                const uint4 val = *reinterpret_cast<const uint4*>(gs + r * 64 + ((c ^ (r >> 1)) & 3) * 16);
+                *reinterpret_cast<uint4*>(g_base + static_cast<long long>(r) * p.Vp + c * 8) = val;
+              }
+            } else {
+              // (memory-lean variant, no room for the stage: 64 bytes per row straight from the owning thread)
+              uint4* dst = reinterpret_cast<uint4*>(g_row + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = w4[q];
+              // the two columns with one-hot terms are patched afterwards (same thread, program order): their softmax
+              // probabilities are exp(lp) from the forward, so no per-element comparison is needed in the loop above
+              if (static_cast<unsigned>(p.blank - col0) < 32u) g_row[p.blank] = __float2half_rn(g_blank);
+              if (static_cast<unsigned>(tgt - col0) < 32u) g_row[tgt] = __float2half_rn(g_tgt);
+            }
           }
         }
         tc_fence_before();
