@@ -121,8 +121,9 @@ int rnnt_b200_joint_argmax(const float* enc_rows, int64_t enc_stride, const floa
  * tokens (B, max_len) int32 receives the emitted tokens, n_tokens (B) = 1 + their count (the seed blank is counted,
  * as rnnt/model.py:53,64 does).  margins_out (optional, (T+max_len+2, B) fp32, caller-initialised) receives the top-2
  * logit gap at [step, b] for every step utterance b was active in.  scratch: rnnt_b200_greedy_decode_scratch_bytes
- * bytes, 128-byte aligned; its first 64 bytes return eight int64 counters (cycles of phases P1..P6, joint steps taken,
- * cycles in grid barriers) of CTA 0. */
+ * bytes, 128-byte aligned (it also holds two per-symbol tables built at kernel start: LayerNorm(embedding), (V, E), and
+ * conv1's tap products of it, (V, 3E) floats); its first 64 bytes return eight int64 counters of CTA 0 (cycles of
+ * phases P1, P2, P3, the one-off conv1 table build, P5, P6, joint steps taken, cycles in grid barriers). */
 size_t rnnt_b200_greedy_decode_scratch_bytes(int B, int H, int V, int E);
 int rnnt_b200_greedy_decode(const float* enc, int64_t enc_sb, int64_t enc_st, const int32_t* T_len,
                             const float* joint_w, const float* joint_b, const float* emb, const float* ln1_w,
